@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""bench.py -- queries/s of the model-scored HNSW retrieval hot path (BASELINE.json metric).
+
+A "step" = one batch of queries through the whole exec.pb dataflow (5 scoring rounds, 4 expand +
+visited-filter rounds, 6 top-k) on synthetic data.  Default workload = BASELINE configs[1]:
+1M items d=128 f32, batch=256 queries, scoring MLP 2x512, ef_search=200
+(level_topn=[100,200,200,200,200,200]), one B200.
+
+  python bench.py --gpus 1 --steps 10 --warmup 3            # this repo's CUDA path
+  python bench.py --impl reference ...                       # the reference algorithm on the host cores
+  torchrun --nproc-per-node N bench.py --gpus N ...          # corpus row-sharded over N GPUs (strong scaling)
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import hashlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+EF_TOPN = {200: [100, 200, 200, 200, 200, 200],      # reference README.md:216
+           400: [100, 200, 400, 400, 400, 200]}      # NANN_impls/nann/benchmark/gen_runmeta.py:23
+MAC_PER_ROW = 256 * 512 + 512 * 512 + 512            # un-hoisted algorithmic count
+ROW_BYTES = 512
+CACHE = os.environ.get("NANN_BENCH_CACHE", "/tmp/nann_b200_bench_cache")
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d.get("hbm_gbs", 6650.0), tf_burst=d.get("bf16_tflops", 1590.0),
+                    tf_sustained=d.get("bf16_tflops_sustained", 1400.0), source="measured")
+    return dict(hbm_gbs=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+# ------------------------------------------------------------------------------------------------
+# workload: corpus shard + HNSW files (cached on local disk so both arms of a box reuse them)
+# ------------------------------------------------------------------------------------------------
+def shard_bounds(n, world, rank):
+    per = (n + world - 1) // world
+    lo = min(rank * per, n)
+    return lo, min(lo + per, n)
+
+
+def get_shard(n_items, world, rank, device):
+    """-> dict(emb, item_ids (GLOBAL ids), ep, values, row_splits) for this rank's row range."""
+    from nann_b200 import index as nix
+    key = hashlib.sha1(json.dumps([n_items, world, rank, 128, 32, 4, "v3"]).encode()).hexdigest()[:16]
+    root = os.path.join(CACHE, f"shard_{n_items}_{world}_{rank}_{key}")
+    embs_dir, index_dir = os.path.join(root, "embeddings"), os.path.join(root, "index")
+    if not os.path.exists(os.path.join(root, "done")):
+        t = time.time()
+        full = nix.synthetic_corpus(n_items, 128, seed=0)
+        ids = nix.synthetic_item_ids(n_items, seed=1)
+        lo, hi = shard_bounds(n_items, world, rank)
+        emb = np.ascontiguousarray(full[lo:hi])
+        g = nix.build_hnsw(emb, M=32, start_level=2, seed=4 + rank, device=device)
+        nix.save_index(embs_dir, index_dir, emb, ids[lo:hi], g)
+        open(os.path.join(root, "done"), "w").write("ok")
+        log(f"[bench] rank {rank}: built HNSW over rows [{lo},{hi}) in {time.time() - t:.1f}s on {device}")
+    emb, item_ids, g = nix.load_index_arrays(embs_dir, index_dir)
+    return dict(emb=emb, item_ids=item_ids, ep=g["enter_points"], values=g["values"], row_splits=g["row_splits"],
+                embs_dir=embs_dir, index_dir=index_dir)
+
+
+def shard_topn(T, world):
+    """per-shard beam widths when the corpus is split `world` ways: ceil(T/world), floored so that
+    every TopKV2 still has its k candidates ('per-shard level_topn tuned down')."""
+    if world == 1:
+        return list(T)
+    t = [max(-(-x // world), 8) for x in T[:5]]
+    k = min(max(-(-T[5] // world) * 2, 16), sum(t[1:5]))
+    return t + [k]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.12)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx = max(mx, float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args, T, rank, world):
+    """The reference algorithm (CPU custom-op path restated in oracle/) on the host cores:
+    batch=1 per request, one in-flight request per core (blaze-benchmark consumers)."""
+    if rank != 0:
+        return None
+    import torch
+    from oracle import oracle as orc
+    from nann_b200 import index as nix, scorer_weights as sw
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    sh = get_shard(args.n_items, 1, 0, dev)
+    cores = os.cpu_count() or 1
+    oix = orc.Index(sh["emb"], sh["item_ids"], sh["ep"].astype(np.int32), [v.astype(np.int32) for v in sh["values"]], sh["row_splits"])
+    om = orc.Mlp(*sw.mlp_weights(seed=3))
+    sample_q = args.cpu_sample or int(min(args.batch, max(32, 4 * cores)))
+    queries = nix.synthetic_queries(sh["emb"], sample_q * (args.steps + args.warmup), seed=2)
+    for w in range(args.warmup):
+        oix.search_batch_mlp(om, queries[w * sample_q:(w + 1) * sample_q], T, nthreads=cores)
+    secs, rows = 0.0, 0
+    for s in range(args.steps):
+        o = (args.warmup + s) * sample_q
+        r = oix.search_batch_mlp(om, queries[o:o + sample_q], T, nthreads=cores)
+        secs += r["seconds"]; rows += r["n_scored"]
+        assert np.all(r["status"] == 0)
+    qps = sample_q * args.steps / secs
+    sample = f"{sample_q} queries/step (of the {args.batch}-query batch), {args.steps} steps, one request per core"
+    return {"impl": "reference", "metric": "queries/sec at fixed recall@200", "value": qps, "unit": "queries/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000.0 * secs / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, T, 1),
+            "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample,
+                             "rows_scored_per_query": rows / (sample_q * args.steps)},
+            "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+def workload_config(args, T, world):
+    return {"workload": f"{args.n_items} items d=128 f32, batch={args.batch} queries, scoring MLP 2x512, "
+                        f"ef_search={args.ef}, HNSW M=32 (BASELINE configs[1])",
+            "level_topn": list(T), "parallelism": "1 GPU" if world == 1 else f"corpus row-sharded x{world}, NCCL allgather + merge",
+            "l2": "inputs larger than L2: 512 MB embedding table + 260 MB graph per 1M rows, fresh queries every step"}
+
+
+def run_b200(args, T, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import nann_b200 as nb
+    from nann_b200 import index as nix, scorer_weights as sw
+    torch.cuda.set_device(local_rank)
+    dev = f"cuda:{local_rank}"
+    sh = get_shard(args.n_items, world, rank, dev)
+    Ts = shard_topn(T, world)
+    ix = nb.Index.from_arrays(sh["emb"], sh["item_ids"], sh["ep"], sh["values"], sh["row_splits"], device=local_rank)
+    sc = nb.Scorer.mlp(*sw.mlp_weights(seed=3), device=local_rank)
+    if args.precision == "tensor":
+        sc.set_precision(nb.SCORER_TENSOR)
+    se = nb.Searcher(ix, sc, args.batch, Ts)
+    B, k_s, k = args.batch, Ts[5], T[5]
+    n_steps = args.warmup + args.steps
+    # queries are drawn from the FULL corpus so that every rank sees the same ones
+    full = nix.synthetic_corpus(args.n_items, 128, seed=0) if world > 1 else sh["emb"]
+    queries = nix.synthetic_queries(full, B * n_steps, seed=2)
+    q_dev = torch.from_numpy(queries).to(dev)
+    q_pin = torch.from_numpy(queries).pin_memory()
+    ids_d = torch.empty((B, k_s), dtype=torch.int64, device=dev)
+    sc_d = torch.empty((B, k_s), dtype=torch.float32, device=dev)
+    if world > 1:
+        g_ids = torch.empty((world, B, k_s), dtype=torch.int64, device=dev)
+        g_sc = torch.empty((world, B, k_s), dtype=torch.float32, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def step_device(i):
+        status, _ = se.search_device(q_dev[i * B:(i + 1) * B], Ts, ids_d, sc_d, stream=stream)
+        if world > 1:
+            dist.all_gather_into_tensor(g_sc, sc_d)
+            dist.all_gather_into_tensor(g_ids, ids_d)
+            return nb.merge_topk(g_sc, g_ids, k)
+        return status
+
+    def step_e2e(i):
+        # host buffers in, host results out: H2D of the queries and D2H of ids+scores inside the call
+        r = se.search(q_pin[i * B:(i + 1) * B].numpy(), Ts)
+        if world > 1:
+            dist.all_gather_into_tensor(g_sc, torch.from_numpy(r["scores"]).to(dev))
+            dist.all_gather_into_tensor(g_ids, torch.from_numpy(r["ids"]).to(dev))
+            return nb.merge_topk(g_sc, g_ids, k)
+        return r
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, profile):
+        for w in range(args.warmup):
+            fn(w)
+        barrier()
+        se.set_profile(profile)
+        l0 = nb.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for s in range(args.steps):
+            fn(args.warmup + s)
+        e1.record(stream)
+        barrier()
+        wall = time.perf_counter() - t0
+        dev_ms = e0.elapsed_time(e1)
+        prof = se.profile() if profile else None
+        se.set_profile(False)
+        t = torch.tensor([dev_ms, wall * 1000.0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t[0].item(), t[1].item(), nb.launch_count() - l0, prof
+
+    with ClockSampler(local_rank) as clk:
+        dev_ms, _, launches, prof = timed(step_device, True)
+    e2e_dev_ms, e2e_wall_ms, _, _ = timed(step_e2e, False)
+
+    # ---- outside the timed region: recall@200 vs brute force under the same scorer; parity vs the CPU port
+    extra = {}
+    try:
+        n_eval = min(args.eval_queries, B)
+        res = step_e2e(0)
+        got_ids = (res[1] if world > 1 else res["ids"])[:n_eval]
+        emb_t = torch.from_numpy(full).to(dev)          # whole corpus (== this shard when world == 1)
+        all_ids = nix.synthetic_item_ids(args.n_items, seed=1) if world > 1 else sh["item_ids"]
+        hits = 0
+        for q in range(n_eval):
+            s_all = nb.blaze_xla_op(sc, queries[q], emb_t)                 # scores of the WHOLE corpus
+            top = np.argpartition(-s_all, k)[:k]
+            hits += len(set(all_ids[top].tolist()) & set(got_ids[q].tolist()))
+        del emb_t
+        extra["recall_at_k_vs_bruteforce"] = hits / (n_eval * k)
+        extra["recall_queries"] = n_eval
+    except Exception as e:  # never lose the bench line over the side measurements
+        extra["recall_error"] = repr(e)[:200]
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        try:
+            from oracle import oracle as orc
+            cores = os.cpu_count() or 1
+            sh1 = sh if world == 1 else get_shard(args.n_items, 1, 0, dev)
+            oix = orc.Index(sh1["emb"], sh1["item_ids"], sh1["ep"].astype(np.int32), [v.astype(np.int32) for v in sh1["values"]], sh1["row_splits"])
+            om = orc.Mlp(*sw.mlp_weights(seed=3))
+            sample_q = args.cpu_sample or int(min(B, max(32, 4 * cores)))
+            oix.search_batch_mlp(om, queries[:min(sample_q, 2 * cores)], T, nthreads=cores)   # warm
+            r = oix.search_batch_mlp(om, queries[:sample_q], T, nthreads=cores)
+            cpu = {"value": sample_q / r["seconds"], "unit": "queries/s", "cores": cores, "kind": "port",
+                   "sample": f"first {sample_q} queries of step 0, one request per core, {r['seconds']:.1f}s",
+                   "rows_scored_per_query": r["n_scored"] / sample_q}
+            if world == 1:
+                mine = se.search(queries[:sample_q], T)
+                cpu["ids_equal_to_gpu"] = bool(np.array_equal(mine["ids"], r["ids"]))
+                cpu["max_abs_score_diff"] = float(np.abs(mine["scores"] - r["scores"]).max())
+        except Exception as e:
+            cpu = {"error": repr(e)[:200]}
+    if rank != 0:
+        return None
+
+    pk = peaks()
+    qps = B * args.steps / (dev_ms / 1000.0)
+    rows = prof["rows_scored"]
+    score_ms = prof["ms"]["score"]
+    n_score = max(prof["launches"]["score"], 1)
+    ach_tf = rows * 2.0 * MAC_PER_ROW / (score_ms / 1000.0) / 1e12 if score_ms > 0 else 0.0
+    stage_tot = sum(prof["ms"].values())
+    out = {
+        "metric": "queries/sec at fixed recall@200", "value": qps, "unit": "queries/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": dict(workload_config(args, T, world), shard_level_topn=Ts, scorer_precision=args.precision),
+        "e2e": {"value": B * args.steps / (e2e_wall_ms / 1000.0), "unit": "queries/s",
+                "h2d_bytes_per_step": B * 128 * 4, "d2h_bytes_per_step": B * k_s * 12 + B * 4 + 10 * B * 4,
+                "timing": "wall clock around the public API call with pinned host inputs and host outputs",
+                "device_ms_per_step": e2e_dev_ms / args.steps},
+        "gpu_launches": launches,
+        "clocks": clk.summary(),
+        "roofline": {
+            "kernel": "mlp_exact_kernel (fused row gather + 2x512 MLP, fp32 FFMA)" if args.precision == "exact"
+                      else "mlp_tc_kernel (fused row gather + 2x512 MLP, tcgen05 fp16-split)",
+            "bound": "tensor", "achieved": ach_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+            "frac": ach_tf / pk["tf_sustained"], "peak_source": f"bf16 dense sustained, of {pk['source']}",
+            "traffic": None,
+            "algorithmic_flops_per_row": 2 * MAC_PER_ROW, "rows_per_launch": rows / n_score,
+            "avg_launch_ms": score_ms / n_score,
+            "gather_GBps_inside_kernel": rows * ROW_BYTES / (score_ms / 1000.0) / 1e9 if score_ms > 0 else 0.0,
+            "hbm_peak_GBps": pk["hbm_gbs"]},
+        "stages_ms_per_step": {k2: v / args.steps for k2, v in prof["ms"].items()},
+        "stage_share": {k2: (v / stage_tot if stage_tot else 0) for k2, v in prof["ms"].items()},
+        "rows_scored_per_query": rows / (B * args.steps),
+        "cpu_baseline": cpu,
+    }
+    out.update(extra)
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n-items", type=int, default=1_000_000)
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--ef", type=int, default=200, choices=[200, 400])
+    ap.add_argument("--precision", default=os.environ.get("NANN_BENCH_PRECISION", "exact"), choices=["exact", "tensor"])
+    ap.add_argument("--eval-queries", type=int, default=16)
+    ap.add_argument("--cpu-sample", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    T = EF_TOPN[args.ef]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        out = run_reference(args, T, rank, world)
+        if out is not None:
+            print(json.dumps(out), flush=True)
+        return
+
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device; there is no CPU fallback (use --impl reference)")
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    try:
+        out = run_b200(args, T, rank, world, local_rank)
+        if out is not None:
+            print(json.dumps(out), flush=True)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,236 @@
+/*
+ * nann_b200.h -- C ABI of libnann_b200.so: a B200 (sm_100a) implementation of alibaba/nann's
+ * model-scored HNSW retrieval hot path, shaped so the reference's TensorFlow custom-op
+ * boundary can bind it (see INTEGRATION.md for the shim).
+ *
+ * Reference interfaces replaced (paths relative to the reference checkout,
+ * UO = tensorflow/tensorflow/core/user_ops):
+ *   nann_huge_const_*             HugeConstantOp          UO/huge_const_op/huge_const_op.cc:58-252
+ *   nann_group_gather_*           GroupGather<T>::Compute UO/beam_search_op/GroupGather_kernel.cc:18-182
+ *   nann_bitmap_ref_difference_*  BitmapRefDifference<T>  UO/bitmap_op/bitmap_ops.cc:150-257
+ *   nann_topk_v2_f32              TopK<CPU,float> (TopKV2) tensorflow/tensorflow/core/kernels/topk_op.cc:40-230
+ *   nann_gather_rows              GatherV2 as used at NANN_impls/nann/delivery/build_opt_graph.py:92,144
+ *   nann_scorer_* / nann_blaze_xla_run   BlazeXlaOp + BlazeXlaPredictor::Compute
+ *                                 UO/blaze_op/blaze_xla_kernel.cc:24-33,194-258, blaze_xla_predictor.cc:360-459
+ *   nann_index_*, nann_search_*   the whole exec.pb dataflow, build_opt_graph.py:69-160, for a
+ *                                 BATCH of queries in one call (the reference runs batch=1)
+ *   nann_merge_topk               new: per-shard top-k merge after the NCCL allgather
+ *   nann_executor_*               blaze-benchmark's session pool + consumers
+ *                                 blaze-benchmark/benchmark/core/model.cc:128-237, predict_request_consumer.cc:17-54
+ *
+ * Conventions
+ *   - Status: every call returns a tensorflow::error::Code value (0 = OK).  The message a TF
+ *     kernel would put in the Status is available from nann_last_error() (thread local).
+ *   - Memory space: any data pointer may be HOST or DEVICE memory; the library inspects it
+ *     (cudaPointerGetAttributes) and stages host buffers over the device itself.  There is NO CPU
+ *     implementation behind this ABI: without a CUDA device every compute entry point fails with
+ *     NANN_FAILED_PRECONDITION.
+ *   - Streams: `stream` is a cudaStream_t passed as void* (NULL = default stream).  Calls that
+ *     hand results back to host memory synchronise that stream before returning; calls whose
+ *     outputs are device pointers are asynchronous.
+ *   - Data-dependent output sizes (GroupGather, BitmapRefDifference) use an allocator callback,
+ *     the C equivalent of OpKernelContext::allocate_output: the library calls
+ *     alloc(ctx, output_index, n_elems) once per output and writes n_elems elements there.
+ *   - Ownership: the library never frees caller memory; handles are opaque and freed by their
+ *     *_destroy.  All entry points are re-entrant; a handle may be used from several threads as
+ *     long as each call uses its own stream (nann_search_* additionally needs its own searcher).
+ */
+#ifndef NANN_B200_H_
+#define NANN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NANN_B200_ABI_VERSION 1
+
+typedef int nann_status;
+enum {
+  NANN_OK = 0,
+  NANN_INVALID_ARGUMENT = 3,
+  NANN_DEADLINE_EXCEEDED = 4,
+  NANN_NOT_FOUND = 5,
+  NANN_RESOURCE_EXHAUSTED = 8,
+  NANN_FAILED_PRECONDITION = 9,
+  NANN_UNIMPLEMENTED = 12,
+  NANN_INTERNAL = 13
+};
+
+/* dtype codes (the five HugeConst is registered for, huge_const_op.cc:230-252) */
+enum { NANN_F16 = 0, NANN_F32 = 1, NANN_F64 = 2, NANN_I32 = 3, NANN_I64 = 4 };
+
+typedef void* (*nann_alloc_fn)(void* ctx, int output_index, int64_t n_elems);
+
+int nann_abi_version(void);
+const char* nann_last_error(void);
+/* number of CUDA kernels this library has launched since load (process wide) */
+uint64_t nann_kernel_launch_count(void);
+/* device_count, SM count and HBM bytes of `device`; NANN_FAILED_PRECONDITION without a GPU */
+nann_status nann_device_info(int device, int* device_count, int* sm_count, int64_t* hbm_bytes,
+                             int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------
+ * HugeConst: npy file -> tensor (host copy + one cached device copy)
+ * checks and error codes as huge_const_op.cc:85-147: NotFound (open), Unimplemented (fortran
+ * order / dtype), Internal (shape or dtype mismatch; only the header's dims are compared).
+ * device < 0: host only.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct nann_huge_const nann_huge_const_t;
+nann_status nann_huge_const_create(const char* path, int dtype, const int64_t* shape, int rank,
+                                   int device, nann_huge_const_t** out);
+const void* nann_huge_const_host(const nann_huge_const_t* h);
+const void* nann_huge_const_device(const nann_huge_const_t* h);
+int64_t nann_huge_const_bytes(const nann_huge_const_t* h);
+void nann_huge_const_destroy(nann_huge_const_t* h);
+/* header only: dtype code, rank (<=8) and dims of an npy file */
+nann_status nann_npy_peek(const char* path, int* dtype, int* rank, int64_t* shape8);
+
+/* ------------------------------------------------------------------------------------------
+ * GroupGather (GroupGather_kernel.cc:18-42): outputs 0 = ret_values (T), 1 = ret_row_splits (i64)
+ * InvalidArgument "Invalid RaggedTensor ... code: 1|2|3" as :62-67; void inputs -> values=[],
+ * row_splits=[0] (:69-77).  unique!=0 emits each group's distinct values in first-occurrence
+ * order (the reference's order is unordered_set iteration order, i.e. unspecified).
+ * ---------------------------------------------------------------------------------------- */
+nann_status nann_group_gather_i32(const int32_t* params_values, int64_t n_params_values,
+                                  const int64_t* params_row_splits, int64_t n_params_row_splits,
+                                  const int64_t* indices_values, int64_t n_indices_values,
+                                  const int64_t* indices_row_splits, int64_t n_indices_row_splits,
+                                  int unique, nann_alloc_fn alloc, void* alloc_ctx, void* stream);
+nann_status nann_group_gather_i64(const int64_t* params_values, int64_t n_params_values,
+                                  const int64_t* params_row_splits, int64_t n_params_row_splits,
+                                  const int64_t* indices_values, int64_t n_indices_values,
+                                  const int64_t* indices_row_splits, int64_t n_indices_row_splits,
+                                  int unique, nann_alloc_fn alloc, void* alloc_ctx, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * BitmapRefDifference (bitmap_ops.cc:150-167): outputs 0 = c_values (T), 1 = c_row_splits (i64);
+ * idx_flag (int32[n_flags]) is the Ref input: mutated in place and "forwarded" (:179,:238).
+ * Order-preserving test-and-set over ALL groups in order, one shared bitmap (:221-234).
+ * Ids >= 32*n_flags are InvalidArgument here (the reference writes out of bounds, :225-231).
+ * ---------------------------------------------------------------------------------------- */
+nann_status nann_bitmap_ref_difference_i32(const int32_t* idx_next_values, int64_t n_values,
+                                           const int64_t* idx_next_row_splits, int64_t n_row_splits,
+                                           int32_t* idx_flag, int64_t n_flags,
+                                           nann_alloc_fn alloc, void* alloc_ctx, void* stream);
+nann_status nann_bitmap_ref_difference_i64(const int64_t* idx_next_values, int64_t n_values,
+                                           const int64_t* idx_next_row_splits, int64_t n_row_splits,
+                                           int32_t* idx_flag, int64_t n_flags,
+                                           nann_alloc_fn alloc, void* alloc_ctx, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * TopKV2 (topk_op.cc:51-93): input [rows, cols] -> values/indices [rows, k]; value descending,
+ * ties -> smaller index first (:142-150).  InvalidArgument for k<0 (:60-61) and cols<k (:66-69).
+ * sorted==0 is accepted and returns the same (sorted) order, a valid "unsorted" result.
+ * ---------------------------------------------------------------------------------------- */
+nann_status nann_topk_v2_f32(const float* input, int64_t rows, int64_t cols, int32_t k, int sorted,
+                             float* values, int32_t* indices, void* stream);
+
+/* GatherV2 on axis 0: out[i] = table[ids[i]], row_bytes per row (build_opt_graph.py:92,144).
+ * InvalidArgument when an id is outside [0, n_rows). */
+nann_status nann_gather_rows(const void* table, int64_t n_rows, int64_t row_bytes,
+                             const int32_t* ids, int64_t n, void* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Scorer = what BlazeXlaOp runs (a nested session over frozen_graph.pb in the reference).
+ *   mlp:        s(u,x) = w3 . relu(W2 . relu(W1 [u;x] + b1) + b2)   (BASELINE configs 2-5)
+ *               W1 [H][2d] row-major (cols 0..d-1 act on u), W2 [H][H], w3 [H]; d=128, H=512.
+ *   attention:  Model.forward, NANN_impls/nann/model/model.py:189-233 (config 1); weights as one
+ *               fp32 blob in the order documented in nann_b200/scorer_weights.py (BN folded).
+ * precision: NANN_SCORER_EXACT  = fp32 FFMA, every dot a sequential chain in k (bit-identical
+ *                                 to the oracle's definition);
+ *            NANN_SCORER_TENSOR = tcgen05 tensor cores, fp16 hi/lo split operands, fp32
+ *                                 accumulate (|score - exact| <= 1e-5); mlp only.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct nann_scorer nann_scorer_t;
+enum { NANN_SCORER_EXACT = 0, NANN_SCORER_TENSOR = 1 };
+nann_status nann_scorer_create_mlp(int d, int H, const float* W1, const float* b1, const float* W2,
+                                   const float* b2, const float* w3, int device, nann_scorer_t** out);
+nann_status nann_scorer_create_attention(const float* blob, int64_t n_floats, int device,
+                                         nann_scorer_t** out);
+int64_t nann_scorer_attention_blob_size(void);
+nann_status nann_scorer_set_precision(nann_scorer_t* s, int precision);
+int nann_scorer_user_floats(const nann_scorer_t* s);  /* 128 (mlp) or 3200 (attention) */
+int nann_scorer_item_dim(const nann_scorer_t* s);     /* 128 or 64 */
+void nann_scorer_destroy(nann_scorer_t* s);
+/* BlazeXlaOp::Compute with inputs [user, item_emb[n, d]] -> logits[n] (fp32 in, fp32 out) */
+nann_status nann_blaze_xla_run(nann_scorer_t* s, const float* user, const float* item_emb, int64_t n,
+                               float* logits, void* stream);
+/* fused GatherV2 + BlazeXlaOp: logits[i] = score(user, table[ids[i]]); table f32 [n_rows][d] */
+nann_status nann_scorer_run_ids(nann_scorer_t* s, const float* user, const float* table,
+                                int64_t n_rows, const int32_t* ids, int64_t n, float* logits,
+                                void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Index: the Appendix-C files (build_hnsw_index.py:33-67) resident in HBM.
+ *   emb f32[n_items][dim] (f16 accepted via emb_dtype, widened once), item_ids i64[n_items],
+ *   enter_points (i32 or i64, ascending, unique), per level l in {0,1}: CSR values (i32 or i64,
+ *   narrowed once like build_opt_graph.py:87) + row_splits i64[n_items+1].
+ * Arrays may be host or device pointers; the index keeps its own device copy.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct nann_index nann_index_t;
+nann_status nann_index_create(int64_t n_items, int dim, const void* emb, int emb_dtype,
+                              const int64_t* item_ids, const void* enter_points, int ep_dtype,
+                              int64_t n_enter_points, const void* const nbr_values[2],
+                              int nbr_dtype, const int64_t* const nbr_row_splits[2], int device,
+                              nann_index_t** out);
+/* loads item_embs.npy, item_ids.npy from embs_dir and enter_points.npy,
+ * neighbors_level_{0,1}_{values,row_splits}.npy from index_dir through nann_huge_const_create */
+nann_status nann_index_load(const char* embs_dir, const char* index_dir, int device,
+                            nann_index_t** out);
+int64_t nann_index_n_items(const nann_index_t* ix);
+int nann_index_dim(const nann_index_t* ix);
+int64_t nann_index_n_enter_points(const nann_index_t* ix);
+const float* nann_index_emb_device(const nann_index_t* ix);
+void nann_index_destroy(nann_index_t* ix);
+
+/* ------------------------------------------------------------------------------------------
+ * Search: exec.pb's dataflow (build_opt_graph.py:109-149) for B queries per call, all on device.
+ * level_topn[6] is a per-call input like the reference's placeholder (:75), shared by the batch.
+ * Per query q: out_item_ids[q][0..k) (k = level_topn[5], i64, the op's 'top_k' output :149),
+ * out_scores[q][0..k) (additional), out_status[q] = NANN_OK or NANN_INVALID_ARGUMENT where the
+ * reference's session.run would fail (TopKV2 n<k, topk_op.cc:66-69; exactly one candidate to
+ * score, the squeeze-to-scalar case of build_opt_graph.py:107).
+ * users: [B][nann_scorer_user_floats].  Host or device pointers throughout.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct nann_searcher nann_searcher_t;
+typedef struct {
+  int64_t n_scored[5];    /* rows scored per round, summed over the batch (main.py:179-185) */
+  int64_t n_expanded[5];  /* ids GroupGather produced per round (level 2: enter points) */
+  int64_t n_failed;       /* queries with status != OK */
+} nann_search_stats_t;
+nann_status nann_searcher_create(const nann_index_t* ix, nann_scorer_t* scorer, int max_batch,
+                                 const int32_t max_level_topn[6], nann_searcher_t** out);
+void nann_searcher_destroy(nann_searcher_t* s);
+/* keep per-round (node ids, scores) of every query for parity checks (costly; off by default) */
+nann_status nann_searcher_set_trace(nann_searcher_t* s, int enable);
+nann_status nann_search_batch(nann_searcher_t* s, const float* users, int B,
+                              const int32_t level_topn[6], int64_t* out_item_ids,
+                              float* out_scores, int32_t* out_status, nann_search_stats_t* stats,
+                              void* stream);
+/* after a traced call: copies round r (0..4) of query q to host: ids/scores capacity cap */
+nann_status nann_searcher_get_trace(nann_searcher_t* s, int q, int round, int32_t* ids,
+                                    float* scores, int64_t cap, int64_t* n);
+/* Stage timing with CUDA events on the launching stream, accumulated over calls while enabled
+ * (enable resets).  stage: 0 = scorer (row gather + model), 1 = expand+filter, 2 = top-k,
+ * 3 = bitmap reset+mark.  rows_scored = rows the scorer processed in those calls. */
+nann_status nann_searcher_set_profile(nann_searcher_t* s, int enable);
+nann_status nann_searcher_get_profile(nann_searcher_t* s, double stage_ms[4], int64_t stage_launches[4],
+                                      int64_t* rows_scored, int64_t* calls);
+/* node ids (rows of the table) of the last call's final top-k, [B][k], before the item_ids gather */
+nann_status nann_searcher_get_nodes(nann_searcher_t* s, int32_t* out_nodes, int64_t cap);
+
+/* ------------------------------------------------------------------------------------------
+ * Shard merge: G per-shard results [G][B][k_in] (score f32, id i64), as laid out by
+ * an allgather, -> global top k_out per query.  Order: score descending, ties -> lower shard,
+ * then lower per-shard rank.  InvalidArgument if G*k_in < k_out.
+ * ---------------------------------------------------------------------------------------- */
+nann_status nann_merge_topk(const float* scores, const int64_t* ids, int G, int B, int k_in,
+                            int k_out, float* out_scores, int64_t* out_ids, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NANN_B200_H_ */

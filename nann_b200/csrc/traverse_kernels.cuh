@@ -1,0 +1,436 @@
+// traverse_kernels.cuh -- the integer side of the hot path on sm_100a:
+//   K3 expand (GroupGather, non-unique)      GroupGather_kernel.cc:136-170
+//   K4 visit filter (BitmapRefDifference)    bitmap_ops.cc:221-234
+//   K5 stable top-k (TopKV2 order)           topk_op.cc:142-150
+//   K1 row gather (GatherV2)                 build_opt_graph.py:92,144
+// All of it is HBM/L2-latency-bound integer work: one warp walks one query's (or one op
+// call's) id list IN ORDER, 32 ids per step, so that "first occurrence wins" and the output
+// order are those of the reference's serial loops by construction.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace nann {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ unsigned lanemask_lt() {
+  unsigned m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+
+// One step of the order-preserving test-and-set over 32 consecutive list elements held one per
+// lane (valid==false for padding lanes).  Returns the number kept; kept elements are written to
+// out[o + rank] in lane order.  bm is this list's bitmap (word = v>>5, bit = v&31).
+// bad is set when v is outside [0, 32*n_words) (caller decides what to do; nothing is written
+// for such a lane).
+template <typename T>
+__device__ __forceinline__ int filter_step(T v, bool valid, uint32_t* bm, int64_t n_words,
+                                           T* out, int64_t o, int* bad) {
+  const unsigned lane = threadIdx.x & 31;
+  bool inrange = valid && v >= 0 && (int64_t)(v >> 5) < n_words;
+  if (valid && !inrange) *bad = 1;
+  // lanes holding the same id: the lowest lane is the first occurrence inside this step
+  unsigned peers = __match_any_sync(FULL, (unsigned long long)(inrange ? (long long)v : -1ll - (long long)lane));
+  bool leader = inrange && ((unsigned)(__ffs(peers) - 1) == lane);
+  bool keep = false;
+  uint32_t bit = 0;
+  uint32_t* wp = nullptr;
+  if (leader) {
+    wp = bm + (int64_t)(v >> 5);
+    bit = 1u << (unsigned)(v & 31);
+    keep = !(ld_cg_u32(wp) & bit);
+  }
+  unsigned keepmask = __ballot_sync(FULL, keep);
+  if (keep) {
+    atomicOr(wp, bit);  // distinct ids may share a word
+    out[o + __popc(keepmask & lanemask_lt())] = v;
+  }
+  __syncwarp();  // orders this step's bitmap writes before the next step's reads
+  return __popc(keepmask);
+}
+
+// ---- batched K3+K4: one warp per query ---------------------------------------------------
+// frontier: f_n node ids per query at frontier + q*f_stride.  Neighbours of the frontier nodes
+// are concatenated in frontier order (GroupGather) and filtered through the query's bitmap
+// (BitmapRefDifference).  out_n[q] = kept, out_exp[q] = ids before filtering.
+__global__ void __launch_bounds__(128)
+expand_filter_kernel(const int32_t* __restrict__ nbr_vals, const int64_t* __restrict__ nbr_rs,
+                     const int32_t* __restrict__ frontier, int64_t f_stride, int f_n,
+                     uint32_t* __restrict__ bitmap, int64_t n_words, int32_t* __restrict__ out_ids,
+                     int64_t out_stride, int32_t* __restrict__ out_n, int32_t* __restrict__ out_exp,
+                     const int32_t* __restrict__ status, int B) {
+  const int q = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
+  const unsigned lane = threadIdx.x & 31;
+  if (q >= B) return;
+  if (status[q] != 0) {
+    if (lane == 0) { out_n[q] = 0; out_exp[q] = 0; }
+    return;
+  }
+  uint32_t* bm = bitmap + (int64_t)q * n_words;
+  int32_t* out = out_ids + (int64_t)q * out_stride;
+  const int32_t* fr = frontier + (int64_t)q * f_stride;
+  int64_t o = 0, expanded = 0;
+  int bad = 0;
+  for (int base = 0; base < f_n; base += 32) {
+    const int fi = base + (int)lane;
+    long long s = 0;
+    int len = 0;
+    if (fi < f_n) {
+      const int32_t node = fr[fi];
+      s = nbr_rs[node];
+      len = (int)(nbr_rs[node + 1] - s);
+    }
+    int incl = len;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int t = __shfl_up_sync(FULL, incl, d);
+      if ((int)lane >= d) incl += t;
+    }
+    const int total = __shfl_sync(FULL, incl, 31);
+    const int excl = incl - len;
+    for (int p0 = 0; p0 < total; p0 += 32) {
+      const int p = p0 + (int)lane;
+      const bool valid = p < total;
+      int j = 0;  // owner = last lane whose exclusive offset is <= p
+#pragma unroll
+      for (int step = 16; step > 0; step >>= 1) {
+        const int cand = j + step;
+        const int e = __shfl_sync(FULL, excl, cand & 31);
+        if (cand < 32 && e <= p) j = cand;
+      }
+      const long long sj = __shfl_sync(FULL, s, j);
+      const int ej = __shfl_sync(FULL, excl, j);
+      int32_t v = valid ? nbr_vals[sj + (p - ej)] : -1;
+      o += filter_step<int32_t>(v, valid, bm, n_words, out, o, &bad);
+    }
+    expanded += total;
+  }
+  if (lane == 0) { out_n[q] = (int32_t)o; out_exp[q] = (int32_t)expanded; }
+}
+
+// ---- mark: set the bits of list[q][0..n) (set_difference on a list that is already unique:
+// build_opt_graph.py:119-120,132-133).  One thread per (q, i).
+__global__ void mark_kernel(const int32_t* __restrict__ list, int64_t stride, int n,
+                            uint32_t* __restrict__ bitmap, int64_t n_words,
+                            const int32_t* __restrict__ status, int B) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= (int64_t)B * n) return;
+  const int q = (int)(t / n), i = (int)(t % n);
+  if (status[q] != 0) return;
+  const int32_t v = list[(int64_t)q * stride + i];
+  atomicOr(bitmap + (int64_t)q * n_words + (v >> 5), 1u << (v & 31));
+}
+
+// ---- op-level BitmapRefDifference: ONE warp walks all groups in order ---------------------
+template <typename T>
+__global__ void bitmap_diff_op_kernel(const T* __restrict__ vals, const int64_t* __restrict__ rs,
+                                      int64_t n_groups, uint32_t* __restrict__ bm, int64_t n_words,
+                                      T* __restrict__ out, int64_t* __restrict__ out_rs,
+                                      int* __restrict__ bad_flag) {
+  const unsigned lane = threadIdx.x & 31;
+  int64_t o = 0;
+  int bad = 0;
+  if (lane == 0) out_rs[0] = 0;
+  for (int64_t g = 0; g < n_groups; ++g) {
+    const int64_t b = rs[g], e = rs[g + 1];
+    for (int64_t p0 = b; p0 < e; p0 += 32) {
+      const int64_t p = p0 + lane;
+      const bool valid = p < e;
+      T v = valid ? vals[p] : (T)-1;
+      o += filter_step<T>(v, valid, bm, n_words, out, o, &bad);
+    }
+    if (lane == 0) out_rs[g + 1] = o;
+  }
+  if (bad) *bad_flag = 1;
+}
+
+// ---- op-level GroupGather: count + fill, one warp per group --------------------------------
+template <typename T>
+__global__ void group_gather_count_kernel(const int64_t* __restrict__ prs, int64_t n_prs,
+                                          const int64_t* __restrict__ iv,
+                                          const int64_t* __restrict__ irs, int64_t n_groups,
+                                          int64_t* __restrict__ group_len, int* __restrict__ bad_flag) {
+  const int64_t g = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const unsigned lane = threadIdx.x & 31;
+  if (g >= n_groups) return;
+  long long sum = 0;
+  for (int64_t j = irs[g] + lane; j < irs[g + 1]; j += 32) {
+    const int64_t idx = iv[j];
+    if (idx < 0 || idx + 1 >= n_prs) { *bad_flag = 1; continue; }
+    sum += prs[idx + 1] - prs[idx];
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(FULL, sum, d);
+  if (lane == 0) group_len[g] = sum;
+}
+
+template <typename T>
+__global__ void group_gather_fill_kernel(const T* __restrict__ pv, const int64_t* __restrict__ prs,
+                                         const int64_t* __restrict__ iv,
+                                         const int64_t* __restrict__ irs, int64_t n_groups,
+                                         const int64_t* __restrict__ out_rs, T* __restrict__ out) {
+  const int64_t g = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const unsigned lane = threadIdx.x & 31;
+  if (g >= n_groups) return;
+  int64_t o = out_rs[g];
+  for (int64_t j = irs[g]; j < irs[g + 1]; ++j) {
+    const int64_t idx = iv[j];
+    const int64_t b = prs[idx], e = prs[idx + 1];
+    for (int64_t k = b + lane; k < e; k += 32) out[o + (k - b)] = pv[k];
+    o += e - b;
+  }
+}
+
+// unique=true: first-occurrence order per group; one warp per group, scratch bitmap-free
+// O(len * distinct/32) compare scan (op-level convenience, not on the exec.pb path).
+template <typename T>
+__global__ void group_gather_unique_kernel(const T* __restrict__ pv, const int64_t* __restrict__ prs,
+                                           const int64_t* __restrict__ iv,
+                                           const int64_t* __restrict__ irs, int64_t n_groups,
+                                           const int64_t* __restrict__ cap_rs, T* __restrict__ tmp,
+                                           int64_t* __restrict__ group_len) {
+  const int64_t g = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const unsigned lane = threadIdx.x & 31;
+  if (g >= n_groups) return;
+  T* out = tmp + cap_rs[g];
+  int64_t o = 0;
+  for (int64_t j = irs[g]; j < irs[g + 1]; ++j) {
+    const int64_t idx = iv[j];
+    for (int64_t k = prs[idx]; k < prs[idx + 1]; ++k) {
+      const T v = pv[k];
+      bool seen = false;
+      for (int64_t q = lane; q < o; q += 32) seen |= (out[q] == v);
+      seen = __any_sync(FULL, seen);
+      if (!seen) {
+        if (lane == 0) out[o] = v;
+        ++o;
+        __syncwarp();
+      }
+    }
+  }
+  if (lane == 0) group_len[g] = o;
+}
+
+// ---- K1: row gather, 16-byte vector loads, one warp per row chunk -------------------------
+// row_bytes must be a multiple of 16 for the vector path; the scalar path handles the rest.
+__global__ void gather_rows_vec_kernel(const uint4* __restrict__ table, int64_t n_rows,
+                                       int vec_per_row, const int32_t* __restrict__ ids, int64_t n,
+                                       uint4* __restrict__ out, int* __restrict__ bad_flag) {
+  const int64_t total = n * vec_per_row;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = t / vec_per_row;
+    const int c = (int)(t - r * vec_per_row);
+    const int64_t id = ids[r];
+    if (id < 0 || id >= n_rows) { *bad_flag = 1; continue; }
+    uint4 v;
+    const uint4* src = table + id * vec_per_row + c;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src));
+    out[t] = v;
+  }
+}
+__global__ void gather_rows_bytes_kernel(const uint8_t* __restrict__ table, int64_t n_rows,
+                                         int64_t row_bytes, const int32_t* __restrict__ ids,
+                                         int64_t n, uint8_t* __restrict__ out,
+                                         int* __restrict__ bad_flag) {
+  const int64_t total = n * row_bytes;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = t / row_bytes;
+    const int64_t id = ids[r];
+    if (id < 0 || id >= n_rows) { *bad_flag = 1; continue; }
+    out[t] = table[id * row_bytes + (t - r * row_bytes)];
+  }
+}
+
+// ---- K5: stable top-k --------------------------------------------------------------------
+// Order = TopKV2's stable_comp: larger value first, equal values -> smaller position first
+// (-0.0 == +0.0 as in the float compare).  One CTA per row/query.
+// The row is the concatenation of segment A (a_n elements) and segment B (b_n elements):
+// exactly tf.concat([...]) + TopKV2 + tf.gather(ids, indices) of build_opt_graph.py:52-66,125-127.
+__device__ __forceinline__ uint32_t order_key(float f) {
+  uint32_t u = __float_as_uint(f);
+  if ((u << 1) == 0) u = 0;  // -0.0 -> +0.0
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+struct TopkArgs {
+  const float* a_sc; const int32_t* a_ids; int64_t a_stride; int a_n;        // fixed length
+  const float* b_sc; int64_t b_sc_stride; const int32_t* b_ids; int64_t b_ids_stride;
+  const int32_t* b_n_ptr; int b_n_fixed;                                      // per-row or fixed
+  int k;
+  float* out_sc; int32_t* out_ids; int32_t* out_pos; int64_t out_stride; int64_t out_offset;
+  const int64_t* item_ids; int64_t* out_item_ids; int64_t out_item_stride;    // optional final gather
+  int32_t* status;       // per-row status (nullable): rows with status!=0 are skipped
+  int reject_single;     // b_n==1 -> InvalidArgument (the tf.squeeze scalar case)
+};
+
+constexpr int TOPK_THREADS = 512;
+constexpr int TOPK_MAX_K = 4096;
+
+__device__ __forceinline__ float topk_score_at(const TopkArgs& a, int64_t row, int i) {
+  return i < a.a_n ? a.a_sc[row * a.a_stride + i] : a.b_sc[row * a.b_sc_stride + (i - a.a_n)];
+}
+
+__global__ void __launch_bounds__(TOPK_THREADS)
+topk_kernel(TopkArgs a) {
+  extern __shared__ unsigned long long sel[];  // [kpad] composite keys
+  __shared__ int hist[256];
+  __shared__ uint32_t s_prefix;
+  __shared__ int s_remaining, s_cnt, s_warp_cnt[TOPK_THREADS / 32], s_eq_taken;
+  const int64_t row = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int k = a.k;
+  if (a.status && a.status[row] != 0) return;
+  const int b_n = a.b_n_ptr ? a.b_n_ptr[row] : a.b_n_fixed;
+  const int n = a.a_n + b_n;
+  if (n < k || (a.reject_single && b_n == 1)) {
+    if (tid == 0 && a.status) a.status[row] = NANN_INVALID_ARGUMENT;
+    return;
+  }
+  if (k == 0) return;
+
+  // --- radix select (MSD, 8 bits per pass): key of the k-th best -> s_prefix
+  uint32_t prefix = 0, mask = 0;
+  int remaining = k;
+  for (int pass = 3; pass >= 0; --pass) {
+    if (tid < 256) hist[tid] = 0;
+    __syncthreads();
+    const int shift = pass * 8;
+    for (int i = tid; i < n; i += TOPK_THREADS) {
+      const uint32_t key = order_key(topk_score_at(a, row, i));
+      if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255], 1);
+    }
+    __syncthreads();
+    if (tid < 32) {  // warp 0: suffix scan from bin 255 downwards
+      int carry = 0, found_bin = -1, found_before = 0;
+      for (int blk = 7; blk >= 0; --blk) {
+        const int bin = blk * 32 + (31 - tid);  // lane 0 -> highest bin of the block
+        const int c = hist[bin];
+        int incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          int t = __shfl_up_sync(FULL, incl, d);
+          if (tid >= d) incl += t;
+        }
+        const int before = carry + incl - c;  // elements in strictly higher bins
+        const bool hit = (before < remaining) && (remaining <= before + c);
+        const unsigned hm = __ballot_sync(FULL, hit);
+        if (hm && found_bin < 0) {
+          const int src = __ffs(hm) - 1;
+          found_bin = __shfl_sync(FULL, bin, src);
+          found_before = __shfl_sync(FULL, before, src);
+        }
+        carry += __shfl_sync(FULL, incl, 31);
+      }
+      if (tid == 0) {
+        s_prefix = prefix | ((uint32_t)found_bin << shift);
+        s_remaining = remaining - found_before;
+      }
+    }
+    __syncthreads();
+    prefix = s_prefix;
+    remaining = s_remaining;
+    mask |= 255u << shift;
+    __syncthreads();
+  }
+  const uint32_t thr = prefix;   // key of the k-th element
+  const int eq_take = remaining; // how many elements with key == thr belong to the top k
+  const int n_gt = k - eq_take;
+
+  // --- collect: all keys > thr (any order), then the first eq_take keys == thr by position
+  if (tid == 0) { s_cnt = 0; s_eq_taken = 0; }
+  __syncthreads();
+  for (int i = tid; i < n; i += TOPK_THREADS) {
+    const uint32_t key = order_key(topk_score_at(a, row, i));
+    if (key > thr) {
+      const int slot = atomicAdd(&s_cnt, 1);
+      sel[slot] = ((unsigned long long)(~key) << 32) | (uint32_t)i;
+    }
+  }
+  __syncthreads();
+  {
+    const int lane = tid & 31, wid = tid >> 5;
+    for (int base = 0; base < n; base += TOPK_THREADS) {
+      if (s_eq_taken >= eq_take) break;  // uniform: read after the barrier below / initial sync
+      const int i = base + tid;
+      const bool eq = (i < n) && (order_key(topk_score_at(a, row, i)) == thr);
+      const unsigned bm = __ballot_sync(FULL, eq);
+      if (lane == 0) s_warp_cnt[wid] = __popc(bm);
+      __syncthreads();
+      int before = s_eq_taken;
+      for (int w = 0; w < wid; ++w) before += s_warp_cnt[w];
+      const int rank = before + __popc(bm & lanemask_lt());
+      if (eq && rank < eq_take) sel[n_gt + rank] = ((unsigned long long)(~thr) << 32) | (uint32_t)i;
+      __syncthreads();
+      if (tid == 0) {
+        int tot = 0;
+        for (int w = 0; w < TOPK_THREADS / 32; ++w) tot += s_warp_cnt[w];
+        s_eq_taken += tot;
+      }
+      __syncthreads();
+    }
+  }
+  // --- sort the k selected composites ascending = (value desc, position asc); bitonic in smem
+  int kpad = 1;
+  while (kpad < k) kpad <<= 1;
+  for (int i = k + tid; i < kpad; i += TOPK_THREADS) sel[i] = ~0ull;
+  __syncthreads();
+  for (int size = 2; size <= kpad; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = tid; t < (kpad >> 1); t += TOPK_THREADS) {
+        const int lo = ((t / stride) * (stride << 1)) + (t % stride);
+        const int hi = lo + stride;
+        const bool up = ((lo & size) == 0);
+        const unsigned long long x = sel[lo], y = sel[hi];
+        if ((x > y) == up) { sel[lo] = y; sel[hi] = x; }
+      }
+      __syncthreads();
+    }
+  }
+  // --- emit
+  for (int r = tid; r < k; r += TOPK_THREADS) {
+    const int pos = (int)(uint32_t)(sel[r] & 0xffffffffull);
+    const float sc = topk_score_at(a, row, pos);
+    const int64_t o = row * a.out_stride + a.out_offset + r;
+    if (a.out_sc) a.out_sc[o] = sc;
+    if (a.out_pos) a.out_pos[o] = pos;
+    int32_t id = pos;
+    if (a.a_ids || a.b_ids)
+      id = pos < a.a_n ? a.a_ids[row * a.a_stride + pos] : a.b_ids[row * a.b_ids_stride + (pos - a.a_n)];
+    if (a.out_ids) a.out_ids[o] = id;
+    if (a.out_item_ids) a.out_item_ids[row * a.out_item_stride + r] = a.item_ids[id];
+  }
+}
+
+// ---- K6: G-way shard merge: rows of G*k_in (score,id) in allgather layout [G][B][k_in] ------
+// Same stable top-k with position = g*k_in + r, i.e. ties -> lower shard, then lower rank.
+__global__ void merge_pack_kernel(const float* __restrict__ scores, int G, int B, int k_in,
+                                  float* __restrict__ packed /* [B][G*k_in] */) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t tot = (int64_t)G * B * k_in;
+  if (t >= tot) return;
+  const int r = (int)(t % k_in);
+  const int64_t gb = t / k_in;
+  const int b = (int)(gb % B), g = (int)(gb / B);
+  packed[((int64_t)b * G + g) * k_in + r] = scores[t];
+}
+__global__ void merge_emit_kernel(const int32_t* __restrict__ pos, const int64_t* __restrict__ ids,
+                                  int G, int B, int k_in, int k_out, int64_t* __restrict__ out_ids) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= (int64_t)B * k_out) return;
+  const int b = (int)(t / k_out);
+  const int p = pos[t];
+  const int g = p / k_in, r = p % k_in;
+  out_ids[t] = ids[((int64_t)g * B + b) * k_in + r];
+}
+
+}  // namespace nann

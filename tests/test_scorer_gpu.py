@@ -1,0 +1,71 @@
+"""Scorer parity.  EXACT mlp path: bit-identical to the oracle's fp32 definition.  Attention
+scorer and TENSOR mlp path: |diff| <= 1e-5 (north_star tolerance)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def nb():
+    import nann_b200
+    return nann_b200
+
+
+@pytest.mark.parametrize("n", [2, 63, 64, 65, 1000, 14800])
+def test_mlp_exact_bit_identical(nb, oracle, small_world, n):
+    emb = small_world["emb"]
+    m = oracle.Mlp(*small_world["mlp"])
+    s = nb.Scorer.mlp(*small_world["mlp"])
+    rng = np.random.default_rng(n)
+    ids = rng.integers(0, emb.shape[0], n).astype(np.int32)
+    u = small_world["queries"][n % 64]
+    want = m.score(u, emb, ids)
+    got = nb.score_ids(s, u, emb, ids)                       # fused gather + score
+    np.testing.assert_array_equal(got.view(np.uint32), want.view(np.uint32))
+    got2 = nb.blaze_xla_op(s, u, emb[ids])                   # BlazeXlaOp form: dense item_emb input
+    np.testing.assert_array_equal(got2.view(np.uint32), want.view(np.uint32))
+
+
+def test_mlp_exact_adversarial_values(nb, oracle, small_world):
+    """denormals, large magnitudes, exact zeros: still bit-identical (no FTZ, IEEE fma)."""
+    W1, b1, W2, b2, w3 = [a.copy() for a in small_world["mlp"]]
+    rng = np.random.default_rng(9)
+    x = rng.standard_normal((300, 128)).astype(np.float32)
+    x[:50] *= 1e-38
+    x[50:100] *= 1e4
+    x[100:110] = 0
+    W1[::7] *= 1e-20
+    m = oracle.Mlp(W1, b1, W2, b2, w3)
+    s = nb.Scorer.mlp(W1, b1, W2, b2, w3)
+    u = (rng.standard_normal(128) * 3).astype(np.float32)
+    np.testing.assert_array_equal(nb.blaze_xla_op(s, u, x).view(np.uint32), m.score(u, x).view(np.uint32))
+
+
+def test_attention_scorer(nb, oracle):
+    from nann_b200 import scorer_weights as sw
+    blob = sw.attention_blob(seed=3)
+    a = oracle.Attn(blob)
+    s = nb.Scorer.attention(blob)
+    assert s.user_floats == 3200 and s.item_dim == 64
+    rng = np.random.default_rng(1)
+    user = (0.01 * rng.random((50, 64))).astype(np.float32)          # gen_runmeta.py:28-29
+    table = (rng.standard_normal((4000, 64)) / 8).astype(np.float16).astype(np.float32)   # f16-representable rows
+    for n in (2, 31, 32, 33, 1000):
+        ids = rng.integers(0, 4000, n).astype(np.int32)
+        want = a.score(user, table, ids)
+        got = nb.score_ids(s, user, table, ids)
+        assert np.abs(got - want).max() <= TOL
+        got2 = nb.blaze_xla_op(s, user, table[ids])
+        assert np.abs(got2 - want).max() <= TOL
+    user2 = rng.standard_normal((50, 64)).astype(np.float32)          # O(1) inputs: sharper softmax
+    want = a.score(user2, table, ids)
+    assert np.abs(nb.score_ids(s, user2, table, ids) - want).max() <= TOL * max(1.0, np.abs(want).max())
+
+
+def test_scorer_id_range_check(nb, small_world):
+    s = nb.Scorer.mlp(*small_world["mlp"])
+    with pytest.raises(nb.NannError) as e:
+        nb.score_ids(s, small_world["queries"][0], small_world["emb"][:100], np.array([1, 100], np.int32))
+    assert e.value.code == nb._lib.INVALID_ARGUMENT

@@ -1,0 +1,202 @@
+"""Traversal parity (the exec.pb dataflow, build_opt_graph.py:109-149) on the GPU.
+
+EXACT scorer: the whole search is bit-exact against the oracle -- item ids, ranks, scores and the
+per-round candidate lists.  Independently of the scorer, the integer traversal is checked to be
+bit-exact GIVEN the GPU's own score arrays (oracle re-run fed with the traced GPU scores)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def nb():
+    import nann_b200
+    return nann_b200
+
+
+@pytest.fixture(scope="module")
+def world(nb, small_world, oracle):
+    from tests import util
+    w = dict(small_world)
+    w["ix"] = nb.Index.from_arrays(w["emb"], w["item_ids"], w["ep"], w["values"], w["row_splits"])
+    w["scorer"] = nb.Scorer.mlp(*w["mlp"])
+    w["oix"] = util.oracle_index(oracle, w)
+    w["omlp"] = oracle.Mlp(*w["mlp"])
+    return w
+
+
+def _oracle_batch(world, users, T):
+    return world["oix"].search_batch_mlp(world["omlp"], users, T, nthreads=0)
+
+
+@pytest.mark.parametrize("B", [1, 3, 64])
+def test_search_bit_exact_vs_oracle(nb, world, B):
+    T = world["T"]
+    s = nb.Searcher(world["ix"], world["scorer"], 64, T)
+    users = world["queries"][:B]
+    got = s.search(users, T)
+    want = _oracle_batch(world, users, T)
+    assert np.all(got["status"] == 0) and np.all(want["status"] == 0)
+    np.testing.assert_array_equal(got["ids"], want["ids"])
+    np.testing.assert_array_equal(got["scores"].view(np.uint32), want["scores"].view(np.uint32))
+    assert got["n_scored"].sum() == want["n_scored"]
+
+
+def test_search_trace_matches_oracle_rounds(nb, oracle, world):
+    T = world["T"]
+    s = nb.Searcher(world["ix"], world["scorer"], 8, T)
+    s.set_trace(True)
+    users = world["queries"][8:16]
+    got = s.search(users, T)
+    for q in range(8):
+        u = users[q]
+        ref = world["oix"].search(lambda r, ids: world["omlp"].score(u, world["emb"], ids), T, trace=True)
+        for r in range(5):
+            ids, sc = s.trace(q, r)
+            np.testing.assert_array_equal(ids, ref["trace"][r][0], err_msg=f"q{q} round{r}")
+            np.testing.assert_array_equal(sc.view(np.uint32), ref["trace"][r][1].view(np.uint32))
+        np.testing.assert_array_equal(got["ids"][q], ref["ids"])
+        np.testing.assert_array_equal(s.nodes(8, T[5])[q], ref["nodes"])
+
+
+def test_traversal_bit_exact_given_gpu_scores(nb, world):
+    """Scorer-independent check (used for the tensor-core path too): feed the oracle traversal
+    with the GPU's traced scores; ids/ranks must match exactly."""
+    T = world["T"]
+    s = nb.Searcher(world["ix"], world["scorer"], 4, T)
+    s.set_trace(True)
+    users = world["queries"][20:24]
+    got = s.search(users, T)
+    for q in range(4):
+        traced = [s.trace(q, r) for r in range(5)]
+
+        def score(r, ids, traced=traced):
+            tid, tsc = traced[r]
+            np.testing.assert_array_equal(ids, tid)
+            return tsc
+
+        ref = world["oix"].search(score, T)
+        np.testing.assert_array_equal(got["ids"][q], ref["ids"])
+        np.testing.assert_array_equal(got["scores"][q].view(np.uint32), ref["scores"].view(np.uint32))
+
+
+def test_opwise_path_equals_fused(nb, world):
+    """One C-ABI call per exec.pb node (what the TF shim runs) == the fused batched call."""
+    import torch
+    T = world["T"]
+    s = nb.Searcher(world["ix"], world["scorer"], 2, T)
+    users = world["queries"][30:32]
+    fused = s.search(users, T)
+    emb_dev = torch.from_numpy(world["emb"]).cuda()          # HugeConst's cached device copy
+    vals = [v.astype(np.int32) for v in world["values"]]      # build_opt_graph.py:87 narrows to int32
+    for q in range(2):
+        ids, sc = nb.retrieve_opwise(world["scorer"], users[q], T, emb_dev, world["item_ids"], world["ep"],
+                                     vals, world["row_splits"])
+        assert ids.shape == (1, T[5])
+        np.testing.assert_array_equal(ids[0], fused["ids"][q])
+        np.testing.assert_array_equal(sc.view(np.uint32), fused["scores"][q].view(np.uint32))
+
+
+def test_level_topn_is_a_runtime_input(nb, world):
+    """beam widths change per call without rebuilding anything (build_opt_graph.py:75)."""
+    s = nb.Searcher(world["ix"], world["scorer"], 16, [60, 120, 120, 120, 120, 120])
+    users = world["queries"][:16]
+    for T in ([50, 100, 100, 100, 100, 100], [60, 120, 80, 40, 20, 120], [10, 10, 10, 10, 10, 5], [50, 100, 100, 100, 100, 0]):
+        got = s.search(users, T)
+        want = _oracle_batch(world, users, T)
+        np.testing.assert_array_equal(got["status"], want["status"])
+        np.testing.assert_array_equal(got["ids"], want["ids"])
+    with pytest.raises(nb.NannError):
+        s.search(users, [61, 10, 10, 10, 10, 10])            # above the workspace maximum
+    with pytest.raises(nb.NannError):
+        s.search(users, [10, 10, 10, -1, 10, 10])            # "Need k >= 0"
+
+
+def test_fewer_than_k_candidates_fails_that_query_only(nb, oracle, world):
+    n_ep = len(world["ep"])
+    T = [n_ep + 1, 10, 10, 10, 10, 10]                       # TopKV2: input must have at least k columns
+    s = nb.Searcher(world["ix"], world["scorer"], 4, T)
+    got = s.search(world["queries"][:4], T)
+    want = _oracle_batch(world, world["queries"][:4], T)
+    assert np.all(got["status"] == nb._lib.INVALID_ARGUMENT) and np.all(want["status"] == oracle.INVALID_ARGUMENT)
+    assert np.all(got["ids"] == -1) and got["n_failed"] == 4
+    T2 = [20, 30, 400, 100, 100, 50]                         # fails later, at the first level-0 top-k, for SOME queries
+    s2 = nb.Searcher(world["ix"], world["scorer"], 64, T2)
+    got = s2.search(world["queries"], T2)
+    want = _oracle_batch(world, world["queries"], T2)
+    np.testing.assert_array_equal(got["status"], want["status"])
+    ok = want["status"] == 0
+    np.testing.assert_array_equal(got["ids"][ok], want["ids"][ok])
+
+
+def test_determinism_and_batch_composition(nb, world):
+    T = world["T"]
+    s = nb.Searcher(world["ix"], world["scorer"], 64, T)
+    a = s.search(world["queries"], T)
+    b = s.search(world["queries"], T)
+    np.testing.assert_array_equal(a["ids"], b["ids"])
+    perm = np.random.default_rng(0).permutation(64)
+    c = s.search(world["queries"][perm], T)
+    np.testing.assert_array_equal(c["ids"], a["ids"][perm])   # a query's result does not depend on its batch mates
+    import torch
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        d = s.search(torch.from_numpy(world["queries"]).cuda(), T, stream=st)   # device-resident users, side stream
+    np.testing.assert_array_equal(d["ids"], a["ids"])
+
+
+def test_index_load_from_files_and_dtype_widths(nb, world):
+    """Appendix-C files: i64 values as written by build_hnsw_index.py, or i32 after exec.pb's in-place cast."""
+    T = world["T"]
+    ix2 = nb.Index.load(world["embs_dir"], world["index_dir"])
+    assert ix2.n_items == world["emb"].shape[0] and ix2.dim == 128 and ix2.n_enter_points == len(world["ep"])
+    a = nb.Searcher(ix2, world["scorer"], 8, T).search(world["queries"][:8], T)
+    ix3 = nb.Index.from_arrays(world["emb"], world["item_ids"], world["ep"].astype(np.int32),
+                               [v.astype(np.int32) for v in world["values"]], world["row_splits"])
+    b = nb.Searcher(ix3, world["scorer"], 8, T).search(world["queries"][:8], T)
+    c = nb.Searcher(world["ix"], world["scorer"], 8, T).search(world["queries"][:8], T)
+    np.testing.assert_array_equal(a["ids"], c["ids"])
+    np.testing.assert_array_equal(b["ids"], c["ids"])
+
+
+def test_index_validation(nb, world):
+    bad_vals = [world["values"][0].copy(), world["values"][1]]
+    bad_vals[0][5] = world["emb"].shape[0]                                     # neighbour id out of range
+    with pytest.raises(nb.NannError):
+        nb.Index.from_arrays(world["emb"], world["item_ids"], world["ep"], bad_vals, world["row_splits"])
+    with pytest.raises(nb.NannError):
+        nb.Index.from_arrays(world["emb"], world["item_ids"], world["ep"][::-1].copy(), world["values"], world["row_splits"])
+    rs = [world["row_splits"][0].copy(), world["row_splits"][1]]
+    rs[0][-1] += 1
+    with pytest.raises(nb.NannError):
+        nb.Index.from_arrays(world["emb"], world["item_ids"], world["ep"], world["values"], rs)
+
+
+def test_attention_scorer_search_config1_shapes(nb, oracle):
+    """config 1 plumbing: d=64 f16 table, user [50,64], attention scorer; traversal bit-exact given
+    the GPU scores, scores within 1e-5 of the oracle scorer."""
+    from nann_b200 import index as nix, scorer_weights as sw
+    from tests import util
+    w = util.build_world(tag="c1", n=3000, d=64, M=16, m_levels=6, seed=4, n_cand=40, device="cpu")
+    emb16 = w["emb"].astype(np.float16)
+    blob = sw.attention_blob(seed=3)
+    sc = nb.Scorer.attention(blob)
+    ix = nb.Index.from_arrays(emb16, w["item_ids"], w["ep"], w["values"], w["row_splits"])     # f16 table, widened once
+    T = [20, 40, 40, 40, 40, 40]
+    s = nb.Searcher(ix, sc, 4, T)
+    s.set_trace(True)
+    rng = np.random.default_rng(0)
+    users = (0.01 * rng.random((4, 3200))).astype(np.float16).astype(np.float32)              # comm_seq f16[1,3200]
+    got = s.search(users, T)
+    assert np.all(got["status"] == 0)
+    emb32 = emb16.astype(np.float32)
+    oa = oracle.Attn(blob)
+    oix = oracle.Index(emb32, w["item_ids"], w["ep"].astype(np.int32), [v.astype(np.int32) for v in w["values"]], w["row_splits"])
+    for q in range(4):
+        traced = [s.trace(q, r) for r in range(5)]
+        for r in range(5):
+            want = oa.score(users[q], emb32, traced[r][0])
+            assert np.abs(want - traced[r][1]).max() <= 1e-5
+        ref = oix.search(lambda r, ids, t=traced: t[r][1], T)
+        np.testing.assert_array_equal(got["ids"][q], ref["ids"])
