@@ -1,0 +1,218 @@
+// nann_b200_tf_ops.cc -- the reference-side binding: TensorFlow 1.15 custom ops with the SAME op
+// names, attrs, dtype lists and shape functions as the reference's user_ops, whose kernels forward
+// to libnann_b200.so through include/nann_b200.h.  Built where TensorFlow headers exist (see
+// INTEGRATION.md); not compiled in this repository's image (no TensorFlow, no bazel).
+//
+// Replaces the kernel bodies of
+//   tensorflow/tensorflow/core/user_ops/beam_search_op/GroupGather_kernel.cc:44-182
+//   tensorflow/tensorflow/core/user_ops/bitmap_op/bitmap_ops.cc:170-262 (BitmapRefDifference)
+//   tensorflow/tensorflow/core/user_ops/huge_const_op/huge_const_op.cc:72-252
+//   tensorflow/tensorflow/core/user_ops/blaze_op/blaze_xla_kernel.cc:35-261 (BlazeXlaOp)
+// while the REGISTER_OP blocks stay byte-for-byte what the reference declares, so exec.pb built by
+// NANN_impls/nann/delivery/build_opt_graph.py loads unchanged.  (Drop the reference's own
+// REGISTER_OP/REGISTER_KERNEL_BUILDER for these four ops from //tensorflow/core:user_ops_op_lib, or
+// load this library INSTEAD of linking them: an op name can be registered once.)
+#include "tensorflow/core/framework/op_kernel.h"
+#include "tensorflow/core/framework/shape_inference.h"
+#include "tensorflow/core/framework/tensor.h"
+
+#include "nann_b200.h"
+
+namespace tensorflow {
+namespace {
+
+Status FromNann(nann_status s) {
+  if (s == NANN_OK) return Status::OK();
+  return Status(static_cast<error::Code>(s), nann_last_error());
+}
+
+// allocate_output() behind the C allocator callback
+struct AllocCtx {
+  OpKernelContext* ctx;
+  DataType values_dtype;
+  Status status;
+};
+void* AllocOutput(void* vctx, int index, int64_t n) {
+  auto* a = static_cast<AllocCtx*>(vctx);
+  Tensor* t = nullptr;
+  a->status = a->ctx->allocate_output(index, TensorShape({n}), &t);
+  if (!a->status.ok() || n == 0) return nullptr;
+  return const_cast<char*>(t->tensor_data().data());
+}
+
+// ---- GroupGather: same REGISTER_OP as GroupGather_kernel.cc:18-42 ---------------------------------
+REGISTER_OP("GroupGather")
+    .Input("params_values: T").Input("params_row_splits: int64")
+    .Input("indices_values: int64").Input("indices_row_splits: int64")
+    .Output("ret_values: T").Output("ret_row_splits: int64")
+    .Attr("T: {int32, int64}").Attr("unique: bool = false")
+    .SetShapeFn([](shape_inference::InferenceContext* c) {
+      shape_inference::ShapeHandle h;
+      for (int i = 0; i < 4; ++i) TF_RETURN_IF_ERROR(c->WithRank(c->input(i), 1, &h));
+      if (c->Value(c->Dim(c->input(1), 0)) == 1 || c->Value(c->Dim(c->input(3), 0)) == 1) {
+        c->set_output(0, c->MakeShape({0}));
+        c->set_output(1, c->MakeShape({1}));
+        return Status::OK();
+      }
+      c->set_output(0, c->MakeShape({c->UnknownDim()}));
+      c->set_output(1, c->input(3));
+      return Status::OK();
+    });
+
+template <typename T>
+class GroupGatherB200 : public OpKernel {
+ public:
+  explicit GroupGatherB200(OpKernelConstruction* c) : OpKernel(c) { OP_REQUIRES_OK(c, c->GetAttr("unique", &unique_)); }
+  void Compute(OpKernelContext* ctx) override {
+    const Tensor &pv = ctx->input(0), &prs = ctx->input(1), &iv = ctx->input(2), &irs = ctx->input(3);
+    AllocCtx a{ctx, DataTypeToEnum<T>::value, Status::OK()};
+    nann_status s;
+    if (std::is_same<T, int32>::value)
+      s = nann_group_gather_i32(reinterpret_cast<const int32_t*>(pv.tensor_data().data()), pv.NumElements(),
+                                reinterpret_cast<const int64_t*>(prs.tensor_data().data()), prs.NumElements(),
+                                reinterpret_cast<const int64_t*>(iv.tensor_data().data()), iv.NumElements(),
+                                reinterpret_cast<const int64_t*>(irs.tensor_data().data()), irs.NumElements(),
+                                unique_, AllocOutput, &a, nullptr);
+    else
+      s = nann_group_gather_i64(reinterpret_cast<const int64_t*>(pv.tensor_data().data()), pv.NumElements(),
+                                reinterpret_cast<const int64_t*>(prs.tensor_data().data()), prs.NumElements(),
+                                reinterpret_cast<const int64_t*>(iv.tensor_data().data()), iv.NumElements(),
+                                reinterpret_cast<const int64_t*>(irs.tensor_data().data()), irs.NumElements(),
+                                unique_, AllocOutput, &a, nullptr);
+    OP_REQUIRES_OK(ctx, a.status);
+    OP_REQUIRES_OK(ctx, FromNann(s));
+  }
+ private:
+  bool unique_ = false;
+};
+REGISTER_KERNEL_BUILDER(Name("GroupGather").Device(DEVICE_CPU).TypeConstraint<int32>("T"), GroupGatherB200<int32>);
+REGISTER_KERNEL_BUILDER(Name("GroupGather").Device(DEVICE_CPU).TypeConstraint<int64>("T"), GroupGatherB200<int64>);
+
+// ---- BitmapRefDifference: same REGISTER_OP as bitmap_ops.cc:150-167 --------------------------------
+REGISTER_OP("BitmapRefDifference")
+    .Input("idx_next_values: T").Input("idx_next_row_splits: int64").Input("idx_flag: Ref (int32)")
+    .Output("c_values: T").Output("c_row_splits: int64").Output("idx_flag_new: Ref (int32)")
+    .Attr("T: {int32, int64}")
+    .SetShapeFn([](shape_inference::InferenceContext* c) {
+      shape_inference::ShapeHandle h;
+      for (int i = 0; i < 3; ++i) TF_RETURN_IF_ERROR(c->WithRank(c->input(i), 1, &h));
+      c->set_output(0, c->MakeShape({c->UnknownDim()}));
+      c->set_output(1, c->input(1));
+      c->set_output(2, c->input(2));
+      return Status::OK();
+    });
+
+template <typename T>
+class BitmapRefDifferenceB200 : public OpKernel {
+ public:
+  explicit BitmapRefDifferenceB200(OpKernelConstruction* c) : OpKernel(c) {}
+  void Compute(OpKernelContext* ctx) override {
+    const Tensor &v = ctx->input(0), &rs = ctx->input(1);
+    Tensor flags = ctx->mutable_input(2, /*lock_held=*/false);  // Ref input mutated in place (bitmap_ops.cc:179)
+    AllocCtx a{ctx, DataTypeToEnum<T>::value, Status::OK()};
+    nann_status s;
+    if (std::is_same<T, int32>::value)
+      s = nann_bitmap_ref_difference_i32(reinterpret_cast<const int32_t*>(v.tensor_data().data()), v.NumElements(),
+                                         reinterpret_cast<const int64_t*>(rs.tensor_data().data()), rs.NumElements(),
+                                         flags.flat<int32>().data(), flags.NumElements(), AllocOutput, &a, nullptr);
+    else
+      s = nann_bitmap_ref_difference_i64(reinterpret_cast<const int64_t*>(v.tensor_data().data()), v.NumElements(),
+                                         reinterpret_cast<const int64_t*>(rs.tensor_data().data()), rs.NumElements(),
+                                         flags.flat<int32>().data(), flags.NumElements(), AllocOutput, &a, nullptr);
+    ctx->forward_ref_input_to_ref_output(2, 2);                // bitmap_ops.cc:238
+    OP_REQUIRES_OK(ctx, a.status);
+    OP_REQUIRES_OK(ctx, FromNann(s));
+  }
+};
+REGISTER_KERNEL_BUILDER(Name("BitmapRefDifference").Device(DEVICE_CPU).TypeConstraint<int32>("T"), BitmapRefDifferenceB200<int32>);
+REGISTER_KERNEL_BUILDER(Name("BitmapRefDifference").Device(DEVICE_CPU).TypeConstraint<int64>("T"), BitmapRefDifferenceB200<int64>);
+
+// ---- HugeConst: same REGISTER_OP as huge_const_op.cc:58-70 ----------------------------------------
+REGISTER_OP("HugeConst")
+    .Output("output: dtype").Attr("dtype: type").Attr("shape: shape").Attr("path: string")
+    .SetShapeFn([](shape_inference::InferenceContext* c) {
+      TensorShape shape;
+      TF_RETURN_IF_ERROR(c->GetAttr("shape", &shape));
+      shape_inference::ShapeHandle s;
+      TF_RETURN_IF_ERROR(c->MakeShapeFromTensorShape(shape, &s));
+      c->set_output(0, s);
+      return Status::OK();
+    });
+
+class HugeConstB200 : public OpKernel {
+ public:
+  explicit HugeConstB200(OpKernelConstruction* c) : OpKernel(c) {
+    DataType dt; TensorShape shape; string path;
+    OP_REQUIRES_OK(c, c->GetAttr("dtype", &dt));
+    OP_REQUIRES_OK(c, c->GetAttr("shape", &shape));
+    OP_REQUIRES_OK(c, c->GetAttr("path", &path));
+    int code = dt == DT_HALF ? NANN_F16 : dt == DT_FLOAT ? NANN_F32 : dt == DT_DOUBLE ? NANN_F64
+             : dt == DT_INT32 ? NANN_I32 : dt == DT_INT64 ? NANN_I64 : -1;
+    std::vector<int64_t> dims(shape.dims());
+    for (int i = 0; i < shape.dims(); ++i) dims[i] = shape.dim_size(i);
+    // device 0: the table is cached in HBM once; the host copy backs the CPU-placed output tensor
+    OP_REQUIRES_OK(c, FromNann(nann_huge_const_create(path.c_str(), code, dims.data(), shape.dims(), 0, &h_)));
+    tensor_ = Tensor(dt, shape);
+    std::memcpy(const_cast<char*>(tensor_.tensor_data().data()), nann_huge_const_host(h_), nann_huge_const_bytes(h_));
+  }
+  ~HugeConstB200() override { nann_huge_const_destroy(h_); }
+  void Compute(OpKernelContext* ctx) override { ctx->set_output(0, tensor_); }   // huge_const_op.cc:222
+  bool IsExpensive() override { return false; }
+ private:
+  nann_huge_const_t* h_ = nullptr;
+  Tensor tensor_;
+};
+#define REG_HC(T) REGISTER_KERNEL_BUILDER(Name("HugeConst").Device(DEVICE_CPU).TypeConstraint<T>("dtype"), HugeConstB200)
+REG_HC(Eigen::half); REG_HC(float); REG_HC(double); REG_HC(int32); REG_HC(int64);
+#undef REG_HC
+
+// ---- BlazeXlaOp: same REGISTER_OP as blaze_xla_kernel.cc:24-33 ------------------------------------
+// graph_def / blaze_option_path are accepted and ignored: the scorer weights come from the file named
+// by the NANN_B200_SCORER_WEIGHTS environment variable (an .npy blob written by the weight importer,
+// nann_b200/scorer_weights.py layout); inputs [user_seq_emb f16/f32 [1,50,64], item_emb [n,64]] ->
+// logits f32 [n,1] exactly like the nested session's fetch.
+REGISTER_OP("BlazeXlaOp")
+    .Input("in_tensor: InT").Output("out_tensor: OutT")
+    .Attr("InT: list({int8, int64, float16, float32, int32})")
+    .Attr("OutT: list({int8, int64, float16, float32, int32})")
+    .Attr("input_names: list(string)").Attr("output_names: list(string)")
+    .Attr("graph_def: string").Attr("blaze_option_path: string")
+    .SetShapeFn(shape_inference::UnknownShape);
+
+class BlazeXlaOpB200 : public AsyncOpKernel {
+ public:
+  explicit BlazeXlaOpB200(OpKernelConstruction* c) : AsyncOpKernel(c) {
+    const char* p = std::getenv("NANN_B200_SCORER_WEIGHTS");
+    OP_REQUIRES(c, p != nullptr, errors::NotFound("NANN_B200_SCORER_WEIGHTS is not set"));
+    int64_t n = nann_scorer_attention_blob_size();
+    nann_huge_const_t* blob = nullptr;
+    OP_REQUIRES_OK(c, FromNann(nann_huge_const_create(p, NANN_F32, &n, 1, -1, &blob)));
+    nann_status s = nann_scorer_create_attention(static_cast<const float*>(nann_huge_const_host(blob)), n, 0, &scorer_);
+    nann_huge_const_destroy(blob);
+    OP_REQUIRES_OK(c, FromNann(s));
+  }
+  ~BlazeXlaOpB200() override { nann_scorer_destroy(scorer_); }
+  void ComputeAsync(OpKernelContext* ctx, DoneCallback done) override {
+    Tensor user = ctx->input(0), items = ctx->input(1);
+    Tensor user32, items32;                                     // comm_seq arrives as f16 (build_opt_graph.py:74)
+    auto to_f32 = [&](const Tensor& t, Tensor* out) {
+      if (t.dtype() == DT_FLOAT) { *out = t; return; }
+      *out = Tensor(DT_FLOAT, t.shape());
+      auto src = t.flat<Eigen::half>(); auto dst = out->flat<float>();
+      for (int64 i = 0; i < src.size(); ++i) dst(i) = static_cast<float>(src(i));
+    };
+    to_f32(user, &user32); to_f32(items, &items32);
+    const int64 n = items32.dim_size(0);
+    Tensor* out = nullptr;
+    OP_REQUIRES_OK_ASYNC(ctx, ctx->allocate_output(0, TensorShape({n, 1}), &out), done);
+    OP_REQUIRES_OK_ASYNC(ctx, FromNann(nann_blaze_xla_run(scorer_, user32.flat<float>().data(), items32.flat<float>().data(),
+                                                           n, out->flat<float>().data(), nullptr)), done);
+    done();
+  }
+ private:
+  nann_scorer_t* scorer_ = nullptr;
+};
+REGISTER_KERNEL_BUILDER(Name("BlazeXlaOp").Device(DEVICE_CPU), BlazeXlaOpB200);
+
+}  // namespace
+}  // namespace tensorflow

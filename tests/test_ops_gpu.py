@@ -57,8 +57,11 @@ def test_group_gather_random_vs_oracle(nb, oracle, dt):
     got = nb.group_gather(pv, prs, iv, irs)
     np.testing.assert_array_equal(got[0], want[0])
     np.testing.assert_array_equal(got[1], want[1])
-    wu = oracle.group_gather(pv[:2000] % 97, prs[prs <= 2000], iv[:50] % (np.sum(prs <= 2000) - 1), np.array([0, 20, 50]), unique=True)
-    gu = nb.group_gather(pv[:2000] % 97, prs[prs <= 2000], iv[:50] % (np.sum(prs <= 2000) - 1), np.array([0, 20, 50]), unique=True)
+    cut = int(prs[40])                                  # a valid ragged prefix: rows 0..39
+    sub_pv, sub_prs = pv[:cut] % 97, prs[:41]
+    sub_iv, sub_irs = iv[:50] % 40, np.array([0, 20, 50], np.int64)
+    wu = oracle.group_gather(sub_pv, sub_prs, sub_iv, sub_irs, unique=True)
+    gu = nb.group_gather(sub_pv, sub_prs, sub_iv, sub_irs, unique=True)
     np.testing.assert_array_equal(gu[0], wu[0])       # first-occurrence order on both sides
     np.testing.assert_array_equal(gu[1], wu[1])
 
