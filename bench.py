@@ -50,10 +50,7 @@ def peaks():
 # ------------------------------------------------------------------------------------------------
 # workload: corpus shard + HNSW files (cached on local disk so both arms of a box reuse them)
 # ------------------------------------------------------------------------------------------------
-def shard_bounds(n, world, rank):
-    per = (n + world - 1) // world
-    lo = min(rank * per, n)
-    return lo, min(lo + per, n)
+from nann_b200.distributed import shard_bounds, shard_level_topn as shard_topn  # noqa: E402
 
 
 def get_shard(n_items, world, rank, device):
@@ -75,16 +72,6 @@ def get_shard(n_items, world, rank, device):
     emb, item_ids, g = nix.load_index_arrays(embs_dir, index_dir)
     return dict(emb=emb, item_ids=item_ids, ep=g["enter_points"], values=g["values"], row_splits=g["row_splits"],
                 embs_dir=embs_dir, index_dir=index_dir)
-
-
-def shard_topn(T, world):
-    """per-shard beam widths when the corpus is split `world` ways: ceil(T/world), floored so that
-    every TopKV2 still has its k candidates ('per-shard level_topn tuned down')."""
-    if world == 1:
-        return list(T)
-    t = [max(-(-x // world), 8) for x in T[:5]]
-    k = min(max(-(-T[5] // world) * 2, 16), sum(t[1:5]))
-    return t + [k]
 
 
 class ClockSampler:
@@ -200,8 +187,8 @@ def run_b200(args, T, rank, world, local_rank):
     ids_d = torch.empty((B, k_s), dtype=torch.int64, device=dev)
     sc_d = torch.empty((B, k_s), dtype=torch.float32, device=dev)
     if world > 1:
-        g_ids = torch.empty((world, B, k_s), dtype=torch.int64, device=dev)
-        g_sc = torch.empty((world, B, k_s), dtype=torch.float32, device=dev)
+        g_ids = torch.empty((world * B, k_s), dtype=torch.int64, device=dev)
+        g_sc = torch.empty((world * B, k_s), dtype=torch.float32, device=dev)
     stream = torch.cuda.current_stream()
 
     def step_device(i):
@@ -209,7 +196,7 @@ def run_b200(args, T, rank, world, local_rank):
         if world > 1:
             dist.all_gather_into_tensor(g_sc, sc_d)
             dist.all_gather_into_tensor(g_ids, ids_d)
-            return nb.merge_topk(g_sc, g_ids, k)
+            return nb.merge_topk(g_sc.view(world, B, k_s), g_ids.view(world, B, k_s), k)
         return status
 
     def step_e2e(i):
@@ -218,7 +205,7 @@ def run_b200(args, T, rank, world, local_rank):
         if world > 1:
             dist.all_gather_into_tensor(g_sc, torch.from_numpy(r["scores"]).to(dev))
             dist.all_gather_into_tensor(g_ids, torch.from_numpy(r["ids"]).to(dev))
-            return nb.merge_topk(g_sc, g_ids, k)
+            return nb.merge_topk(g_sc.view(world, B, k_s), g_ids.view(world, B, k_s), k)
         return r
 
     def barrier():

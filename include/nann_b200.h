@@ -230,6 +230,42 @@ nann_status nann_searcher_get_nodes(nann_searcher_t* s, int32_t* out_nodes, int6
 nann_status nann_merge_topk(const float* scores, const int64_t* ids, int G, int B, int k_in,
                             int k_out, float* out_scores, int64_t* out_ids, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Executor: blaze-benchmark's load generator + session pool around the search call
+ * (blaze-benchmark/benchmark/proto/bench_conf.proto:5-42; core/benchmark.cc:101-146;
+ * core/model.cc:19-53,192-234; core/predict_request_consumer.cc:17-54; core/metrics.cc:5-94).
+ * predictor_num searchers, each with its own CUDA stream and consumer thread, replace the
+ * reference's sessions on virtual GPUs / CUDA contexts; a consumer coalesces up to max_batch_size
+ * queued requests into one nann_search_batch call (1 = the reference: one run per request).
+ * Histograms are {count,min,max,mean,stddev,median,p75,p95,p98,p99,p99.9} like cppmetrics'
+ * ConsoleReporter; latency_us = duration of the run a request was part of (what the reference
+ * records), e2e_latency_us = enqueue -> completion.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  int predictor_num;       /* bench_conf.proto:21-22 */
+  int bench_thread_count;  /* :36-37 producer threads */
+  double duration_s;       /* :38-39 */
+  int qps;                 /* :23-24, <= 0 = maximum (closed loop) */
+  int max_queue_size;      /* :40-41, <= 0 never drop */
+  int max_batch_size;      /* new: dynamic batching width */
+  int batch_timeout_us;    /* new: how long a consumer waits for a fuller batch (0 = take what is queued) */
+  int report_interval_s;   /* 3 s in the reference (metrics.cc:15) */
+} nann_bench_conf_t;
+typedef struct {
+  double seconds;
+  int64_t throughput_count;        /* "<model>_throughput" meter */
+  double mean_rate;                /* events/second */
+  int64_t failures;                /* "<model>_failures" */
+  int64_t get_predictor_failures;  /* "<model>_get_predictor_failures" (dropped: queue too long) */
+  double latency_us[11];
+  double e2e_latency_us[11];
+  double batchsize[11];
+} nann_bench_report_t;
+/* queries: HOST memory [n_queries][user_floats], replayed round-robin like mock.runmeta */
+nann_status nann_executor_run(const nann_index_t* ix, nann_scorer_t* scorer, const nann_bench_conf_t* conf,
+                              const int32_t level_topn[6], const float* queries, int64_t n_queries,
+                              int print_reports, nann_bench_report_t* report);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,3 +16,4 @@
 #include "lib_core.inl"
 #include "lib_ops.inl"
 #include "lib_search.inl"
+#include "lib_executor.inl"

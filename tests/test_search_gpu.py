@@ -200,3 +200,21 @@ def test_attention_scorer_search_config1_shapes(nb, oracle):
             assert np.abs(want - traced[r][1]).max() <= 1e-5
         ref = oix.search(lambda r, ids, t=traced: t[r][1], T)
         np.testing.assert_array_equal(got["ids"][q], ref["ids"])
+
+
+def test_executor_closed_loop(nb, world):
+    """blaze-benchmark role: predictor_num searchers/streams, dynamic batching, cppmetrics-style report."""
+    from nann_b200 import harness
+    T = world["T"]
+    r1 = harness.run_benchmark(world["ix"], world["scorer"], T, world["queries"], predictor_num=2, bench_thread_count=2,
+                               duration=1.0, max_batch_size=1)
+    assert r1["failures"] == 0 and r1["throughput_count"] > 0
+    assert r1["batchsize"]["max"] == 1 and r1["latency_us"]["median"] > 0          # the reference's batch=1 mode
+    r2 = harness.run_benchmark(world["ix"], world["scorer"], T, world["queries"], predictor_num=2, bench_thread_count=2,
+                               duration=1.0, max_batch_size=32)
+    assert r2["failures"] == 0 and r2["batchsize"]["max"] <= 32 and r2["batchsize"]["mean"] > 1
+    assert r2["throughput"] > r1["throughput"]                                      # batching is the throughput lever
+    assert r2["latency_us"]["p99"] >= r2["latency_us"]["median"] >= r2["latency_us"]["min"]
+    r3 = harness.run_benchmark(world["ix"], world["scorer"], T, world["queries"], predictor_num=1, bench_thread_count=1,
+                               duration=1.0, qps=200, max_batch_size=8)
+    assert 100 <= r3["throughput"] <= 260                                           # paced load is respected
