@@ -275,7 +275,20 @@ def run_b200(args, T, rank, world, local_rank):
             if world == 1:
                 mine = se.search(queries[:sample_q], T)
                 cpu["ids_equal_to_gpu"] = bool(np.array_equal(mine["ids"], r["ids"]))
-                cpu["max_abs_score_diff"] = float(np.abs(mine["scores"] - r["scores"]).max())
+                cpu["topk_overlap_with_gpu"] = float(np.mean([len(set(a.tolist()) & set(b.tolist())) / max(k, 1)
+                                                              for a, b in zip(mine["ids"], r["ids"])]))
+                both = [(a, b) for a, b in zip(mine["ids"], r["ids"])]
+                diffs = []
+                for qi, (a, b) in enumerate(both):        # scores of items both paths returned
+                    pa = {int(i): float(s_) for i, s_ in zip(a, mine["scores"][qi])}
+                    diffs += [abs(pa[int(i)] - float(s_)) for i, s_ in zip(b, r["scores"][qi]) if int(i) in pa]
+                cpu["max_abs_score_diff_common_items"] = float(max(diffs)) if diffs else None
+                if args.precision == "tensor":            # the bit-exact path, for the record
+                    sc.set_precision(nb.SCORER_EXACT)
+                    ex = se.search(queries[:sample_q], T)
+                    sc.set_precision(nb.SCORER_TENSOR)
+                    cpu["exact_path_ids_equal_to_cpu"] = bool(np.array_equal(ex["ids"], r["ids"]))
+                    cpu["exact_path_scores_bit_equal"] = bool(np.array_equal(ex["scores"].view(np.uint32), r["scores"].view(np.uint32)))
         except Exception as e:
             cpu = {"error": repr(e)[:200]}
     if rank != 0:
@@ -327,7 +340,7 @@ def main():
     ap.add_argument("--n-items", type=int, default=1_000_000)
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--ef", type=int, default=200, choices=[200, 400])
-    ap.add_argument("--precision", default=os.environ.get("NANN_BENCH_PRECISION", "exact"), choices=["exact", "tensor"])
+    ap.add_argument("--precision", default=os.environ.get("NANN_BENCH_PRECISION", "tensor"), choices=["exact", "tensor"])
     ap.add_argument("--eval-queries", type=int, default=16)
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

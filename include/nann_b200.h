@@ -128,6 +128,19 @@ nann_status nann_bitmap_ref_difference_i64(const int64_t* idx_next_values, int64
 nann_status nann_topk_v2_f32(const float* input, int64_t rows, int64_t cols, int32_t k, int sorted,
                              float* values, int32_t* indices, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * BatchTopKOnRT (UO/topk_op/BatchTopKOnRT_kernel.cc:25-156): ragged per-group top-k.
+ * k: n_k == 1 -> scalar k for every group, else n_k must equal the number of groups (:98-107);
+ * each group yields min(len, k) entries (:117-121).  outputs 0 = values_out (f32),
+ * 1 = idx_out (i64, GROUP-LOCAL positions, :146), 2 = row_splits_out (i64).
+ * ascending != 0 returns the smallest first.  Ties (unspecified by the reference's
+ * std::partial_sort_copy) resolve to the smaller position first, TopKV2's rule.
+ * Void input (row_splits == [0]) -> [], [], [0] (:88-96).
+ * ---------------------------------------------------------------------------------------- */
+nann_status nann_batch_topk_on_rt_f32(const float* values_in, int64_t n_values, const int64_t* row_splits_in,
+                                      int64_t n_row_splits, const int64_t* k, int64_t n_k, int ascending,
+                                      nann_alloc_fn alloc, void* alloc_ctx, void* stream);
+
 /* GatherV2 on axis 0: out[i] = table[ids[i]], row_bytes per row (build_opt_graph.py:92,144).
  * InvalidArgument when an id is outside [0, n_rows). */
 nann_status nann_gather_rows(const void* table, int64_t n_rows, int64_t row_bytes,

@@ -224,6 +224,65 @@ nann_status nann_topk_v2_f32(const float* input, int64_t rows, int64_t cols, int
   return NANN_OK;
 }
 
+nann_status nann_batch_topk_on_rt_f32(const float* values_in, int64_t n_values, const int64_t* row_splits_in,
+                                      int64_t n_row_splits, const int64_t* k, int64_t n_k, int ascending,
+                                      nann_alloc_fn alloc, void* ctx, void* stream) {
+  NANN_TRY(require_device());
+  if (!alloc || !k) return fail(NANN_INVALID_ARGUMENT, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  DevIn<float> d_v;
+  DevIn<int64_t> d_rs;
+  NANN_TRY(d_v.init(values_in, n_values, st));
+  NANN_TRY(d_rs.init(row_splits_in, n_row_splits, st));
+  int code = 0;
+  NANN_TRY(validate_ragged(n_values, d_rs.d, n_row_splits, st, &code));
+  if (code) return fail(NANN_INVALID_ARGUMENT, "Invalid RaggedTensor input, code: %d", code);
+  const int64_t G = n_row_splits - 1;
+  if (G == 0) {                                                    // BatchTopKOnRT_kernel.cc:88-96
+    alloc(ctx, 0, 0); alloc(ctx, 1, 0);
+    int64_t* rs = (int64_t*)alloc(ctx, 2, 1);
+    if (!rs) return fail(NANN_RESOURCE_EXHAUSTED, "allocator returned NULL for output 2");
+    const int64_t zero = 0;
+    if (is_device_ptr(rs)) NANN_CUDA(cudaMemcpy(rs, &zero, 8, cudaMemcpyHostToDevice)); else *rs = 0;
+    return NANN_OK;
+  }
+  if (n_k != 1 && n_k != G)                                        // :103-105
+    return fail(NANN_INVALID_ARGUMENT, "Size of k vector does NOT match number of groups: %lld!=%lld", (long long)n_k, (long long)G);
+  std::vector<int64_t> rs(n_row_splits), kk(G), ors(G + 1);
+  NANN_CUDA(cudaMemcpyAsync(rs.data(), d_rs.d, n_row_splits * 8, cudaMemcpyDeviceToHost, st));
+  std::vector<int64_t> kh(n_k);
+  NANN_CUDA(cudaMemcpyAsync(kh.data(), k, n_k * 8, is_device_ptr(k) ? cudaMemcpyDeviceToHost : cudaMemcpyHostToHost, st));
+  NANN_CUDA(cudaStreamSynchronize(st));
+  ors[0] = 0;
+  int64_t kmax = 0;
+  for (int64_t g = 0; g < G; ++g) {
+    const int64_t len = rs[g + 1] - rs[g];
+    if (len < 0 || len > 0x7fffffff) return fail(NANN_INVALID_ARGUMENT, "Invalid RaggedTensor input: group %lld", (long long)g);
+    kk[g] = std::max<int64_t>(0, std::min(len, n_k == 1 ? kh[0] : kh[g]));   // :117-121
+    kmax = std::max(kmax, kk[g]);
+    ors[g + 1] = ors[g] + kk[g];
+  }
+  if (kmax > TOPK_MAX_K) return fail(NANN_UNIMPLEMENTED, "k=%lld > %d", (long long)kmax, TOPK_MAX_K);
+  const int64_t total = ors[G];
+  DevBuf<int64_t> d_k, d_ors, d_idx;
+  DevBuf<float> d_out;
+  NANN_TRY(d_k.alloc(G)); NANN_TRY(d_ors.alloc(G + 1)); NANN_TRY(d_idx.alloc(std::max<int64_t>(total, 1)));
+  NANN_TRY(d_out.alloc(std::max<int64_t>(total, 1)));
+  NANN_CUDA(cudaMemcpyAsync(d_k.d, kk.data(), G * 8, cudaMemcpyHostToDevice, st));
+  NANN_CUDA(cudaMemcpyAsync(d_ors.d, ors.data(), (G + 1) * 8, cudaMemcpyHostToDevice, st));
+  if (total > 0) {
+    TopkArgs a{};
+    a.b_sc = d_v.d; a.b_row_off = d_rs.d; a.k_ptr = d_k.d; a.k = (int)kmax; a.out_row_off = d_ors.d;
+    a.out_sc = d_out.d; a.out_pos64 = d_idx.d; a.ascending = ascending ? 1 : 0;
+    NANN_LAUNCH(topk_kernel, (unsigned)G, TOPK_THREADS, topk_smem_bytes((int)std::max<int64_t>(kmax, 1)), st, a);
+  }
+  NANN_TRY(deliver<float>(alloc, ctx, 0, d_out.d, total, st));
+  NANN_TRY(deliver<int64_t>(alloc, ctx, 1, d_idx.d, total, st));
+  NANN_TRY(deliver<int64_t>(alloc, ctx, 2, d_ors.d, G + 1, st));
+  NANN_CUDA(cudaStreamSynchronize(st));
+  return NANN_OK;
+}
+
 nann_status nann_gather_rows(const void* table, int64_t n_rows, int64_t row_bytes, const int32_t* ids,
                              int64_t n, void* out, void* stream) {
   NANN_TRY(require_device());

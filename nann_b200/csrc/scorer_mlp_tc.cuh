@@ -315,6 +315,10 @@ mlp_tc_kernel(MlpTcArgs p) {
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
 }
 
+}  // namespace nann
+#include "scorer_mlp_tc2.cuh"
+namespace nann {
+
 // ---- weight images ---------------------------------------------------------------------------------
 // W1 [512][256] row-major (x half = columns 128..255); W2 [512][512] row-major.
 __global__ void tc_build_w1_kernel(const float* __restrict__ W1, __half* __restrict__ img) {
@@ -371,6 +375,7 @@ static nann_status mlp_tc_prepare(nann_scorer* s) {
   NANN_LAUNCH(tc_build_w1_kernel, (512 * 128) / 256, 256, 0, 0, W1.d, st->W1img);
   NANN_LAUNCH(tc_build_w2_kernel, (512 * 512) / 256, 256, 0, 0, W2.d, st->W2img);
   NANN_CUDA(cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+  NANN_CUDA(cudaFuncSetAttribute(mlp_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
   NANN_CUDA(cudaDeviceSynchronize());
   s->tc = st;
   return NANN_OK;
@@ -386,7 +391,10 @@ static nann_status mlp_tc_score(nann_scorer* s, const ScoreCall& c, cudaStream_t
   a.scratch = st->scratch; a.out = c.out; a.out_stride = c.out_stride; a.status = c.status;
   const int64_t n_tiles = (int64_t)a.B * a.tiles_per_q;
   const int grid = (int)std::min<int64_t>(st->n_ctas, n_tiles);
-  NANN_LAUNCH(mlp_tc_kernel, grid, TC_THREADS, TC_SMEM_BYTES, stm, a);
+  // NANN_TC_KERNEL=1 selects the first (bulk-synchronous cp.async) version, kept for A/B runs
+  static const int version = [] { const char* e = std::getenv("NANN_TC_KERNEL"); return e ? atoi(e) : 2; }();
+  if (version == 1) NANN_LAUNCH(mlp_tc_kernel, grid, TC_THREADS, TC_SMEM_BYTES, stm, a);
+  else              NANN_LAUNCH(mlp_tc2_kernel, grid, T2_THREADS, T2_SMEM_BYTES, stm, a);
   return NANN_OK;
 }
 

@@ -120,6 +120,21 @@ def top_k(input, k, sorted=True, stream=None):  # noqa: A002 - tf.math.top_k's a
     return values.reshape(shape[:-1] + (kk,)), indices.reshape(shape[:-1] + (kk,))
 
 
+def batch_top_k_on_rt(values_in, row_splits_in, k, ascending=False, stream=None):
+    """tf.batch_top_k_on_rt (BatchTopKOnRT_kernel.cc:25-48): ragged per-group top-k.
+    k: int or per-group int64 vector.  Returns (values_out f32, idx_out i64 group-local, row_splits_out)."""
+    v, n_v, k0 = _as(values_in, np.float32)
+    rs, n_rs, k1 = _as(row_splits_in, np.int64)
+    kk = np.atleast_1d(np.asarray(k, np.int64))
+    out = _Outputs({0: np.float32, 1: np.int64, 2: np.int64})
+    L = _lib.lib()
+    L.nann_batch_topk_on_rt_f32.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                            C.c_int, _lib.ALLOC_FN, C.c_void_p, C.c_void_p]
+    check(L.nann_batch_topk_on_rt_f32(v, n_v, rs, n_rs, C.c_void_p(kk.ctypes.data), kk.size, int(bool(ascending)),
+                                      out.fn, None, _stream_ptr(stream)))
+    return (out.arrays.get(0, np.empty(0, np.float32)), out.arrays.get(1, np.empty(0, np.int64)), out.arrays[2])
+
+
 def gather(params, indices, stream=None):
     """tf.gather(params, indices) on axis 0 (GatherV2) for a row-major table."""
     idx, n, k0 = _as(indices, np.int32)

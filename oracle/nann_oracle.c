@@ -212,6 +212,48 @@ int orc_topk_v2_f32(const float* input, int64_t rows, int64_t cols, int k, float
 }
 
 /* ------------------------------------------------------------------------------------------
+ * BatchTopKOnRT -- BatchTopKOnRT_kernel.cc:62-156
+ * ---------------------------------------------------------------------------------------- */
+int orc_batch_topk_on_rt_f32(const float* values, int64_t n_values, const int64_t* rs, int64_t n_rs,
+                             const int64_t* k, int64_t n_k, int ascending, float* values_out,
+                             int64_t* idx_out, int64_t* rs_out, int64_t* n_out, int* code) {
+  int valid = orc_validate_ragged(n_values, rs, n_rs);              /* :75-77 */
+  if (code) *code = valid;
+  if (valid != 0) return ORC_INVALID_ARGUMENT;
+  int64_t G = n_rs - 1;
+  rs_out[0] = 0;
+  *n_out = 0;
+  if (G == 0) return ORC_OK;                                        /* :88-96 */
+  if (n_k != 1 && n_k != G) return ORC_INVALID_ARGUMENT;            /* :103-105 */
+  int64_t o = 0;
+  for (int64_t g = 0; g < G; ++g) {
+    int64_t b = rs[g], len = rs[g + 1] - rs[g];
+    int64_t kk = n_k == 1 ? k[0] : k[g];
+    if (kk > len) kk = len;                                         /* :119 */
+    if (kk < 0) kk = 0;
+    /* selection sort of the kk best under (value, position) -- small oracle, clarity over speed */
+    char* used = (char*)calloc((size_t)(len > 0 ? len : 1), 1);
+    for (int64_t r = 0; r < kk; ++r) {
+      int64_t best = -1;
+      for (int64_t i = 0; i < len; ++i) {
+        if (used[i]) continue;
+        if (best < 0) { best = i; continue; }
+        float vi = values[b + i], vb = values[b + best];
+        if (ascending ? (vi < vb) : (vi > vb)) best = i;           /* strict: earlier position wins ties */
+      }
+      used[best] = 1;
+      values_out[o] = values[b + best];
+      idx_out[o] = best;                                            /* group-local (:146) */
+      ++o;
+    }
+    free(used);
+    rs_out[g + 1] = o;
+  }
+  *n_out = o;
+  return ORC_OK;
+}
+
+/* ------------------------------------------------------------------------------------------
  * GatherV2 (stock) as used at build_opt_graph.py:92 (rows) and :144 (item ids)
  * ---------------------------------------------------------------------------------------- */
 void orc_gather_rows_f32(const float* table, int64_t dim, const int32_t* ids, int64_t n, float* out) {

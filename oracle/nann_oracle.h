@@ -74,6 +74,14 @@ int orc_bitmap_ref_difference_i64(const int64_t* v, int64_t n_v, const int64_t* 
 int orc_topk_v2_f32(const float* input, int64_t rows, int64_t cols, int k,
                     float* values, int32_t* indices);
 
+/* ---- BatchTopKOnRT: UO/topk_op/BatchTopKOnRT_kernel.cc:62-156 ------------------------------
+ * k: n_k==1 scalar or one per group; per group min(len,k) results, group-local indices (:146).
+ * The reference's partial_sort_copy leaves tie order unspecified; this restatement breaks ties
+ * by smaller position (a valid instance).  values_out/idx_out need capacity n_values. */
+int orc_batch_topk_on_rt_f32(const float* values, int64_t n_values, const int64_t* rs, int64_t n_rs,
+                             const int64_t* k, int64_t n_k, int ascending, float* values_out,
+                             int64_t* idx_out, int64_t* rs_out, int64_t* n_out, int* code);
+
 /* ---- row gather (stock GatherV2, build_opt_graph.py:92,144) ----------------------------- */
 void orc_gather_rows_f32(const float* table, int64_t dim, const int32_t* ids, int64_t n, float* out);
 void orc_gather_i64(const int64_t* table, const int32_t* ids, int64_t n, int64_t* out);

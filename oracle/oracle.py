@@ -114,6 +114,20 @@ def top_k(inp, k):
     return vals.reshape(shp), idx.reshape(shp)
 
 
+def batch_top_k_on_rt(values, row_splits, k, ascending=False):
+    """Mirrors tf.batch_top_k_on_rt.  Returns (values_out, idx_out (group-local), row_splits_out)."""
+    v, rs = _c(values, np.float32), _c(row_splits, np.int64)
+    kk = np.atleast_1d(np.asarray(k, np.int64))
+    vo, io = np.zeros(max(v.size, 1), np.float32), np.zeros(max(v.size, 1), np.int64)
+    ro = np.zeros(max(rs.size, 1), np.int64)
+    n, code = C.c_int64(0), C.c_int(0)
+    st = lib().orc_batch_topk_on_rt_f32(_p(v), C.c_int64(v.size), _p(rs), C.c_int64(rs.size), _p(kk), C.c_int64(kk.size),
+                                        C.c_int(int(ascending)), _p(vo), _p(io), _p(ro), C.byref(n), C.byref(code))
+    if st != OK:
+        raise OracleError(st, f"code: {code.value}")
+    return vo[:n.value].copy(), io[:n.value].copy(), ro[:max(rs.size, 1)].copy()
+
+
 def huge_const_check(path, dtype, shape, read=False):
     dt = np.dtype(dtype)
     shp = np.asarray(shape, np.int64)

@@ -100,6 +100,23 @@ kat = {
         {"source": "topk_op_test.py:202-208 testKTooLarge", "input": [[0.1, 0.2], [0.3, 0.4]], "k": 4,
          "message": "input must have at least k columns"},
     ],
+    # UO/topk_op/batch_topk_on_rt_test.py:12-17 (print-only; expected values hand-derived from
+    # BatchTopKOnRT_kernel.cc:110-148; all inputs distinct so the unspecified tie order does not matter)
+    "batch_topk_on_rt": {
+        "source": "UO/topk_op/batch_topk_on_rt_test.py:12-17",
+        "values": [1, 2, 3, 4, 5, 6, 7, 11, 12, 13, 14, 15, 21, 22, 23, 24, 25, 26, 27, 31, 32, 33, 34, 35],
+        "row_splits": [0, 7, 12, 19, 24],
+        "calls": [
+            {"k": [3, 2, 3, 2], "ascending": False,
+             "values_out": [7, 6, 5, 15, 14, 27, 26, 25, 35, 34], "idx_out": [6, 5, 4, 4, 3, 6, 5, 4, 4, 3],
+             "row_splits_out": [0, 3, 5, 8, 10]},
+            {"k": 6, "ascending": True,
+             "values_out": [1, 2, 3, 4, 5, 6, 11, 12, 13, 14, 15, 21, 22, 23, 24, 25, 26, 31, 32, 33, 34, 35],
+             "idx_out": [0, 1, 2, 3, 4, 5, 0, 1, 2, 3, 4, 0, 1, 2, 3, 4, 5, 0, 1, 2, 3, 4],
+             "row_splits_out": [0, 6, 11, 17, 22]},
+        ],
+        "void": {"values": [], "row_splits": [0], "k": 3, "values_out": [], "idx_out": [], "row_splits_out": [0]},
+    },
     # UO/huge_const_op/huge_const_test.py:6-27 -- arrays saved then read back through HugeConst
     "huge_const": [
         {"source": "UO/huge_const_op/huge_const_test.py:6,22,25", "dtype": "int32", "array": [[1, 2], [3, 4], [5, 6]]},

@@ -216,3 +216,26 @@ def test_merge_topk(nb, oracle):
     np.testing.assert_array_equal(gi, np.take_along_axis(cat_i, wi.astype(np.int64), 1))
     with pytest.raises(nb.NannError):
         nb.merge_topk(sc[:, :, :10], ids[:, :, :10], 200)
+
+
+def test_batch_topk_on_rt(nb, oracle):
+    c = KAT["batch_topk_on_rt"]
+    for call in c["calls"]:
+        v, i, rs = nb.batch_top_k_on_rt(np.array(c["values"], np.float32), np.array(c["row_splits"], np.int64),
+                                        call["k"], call["ascending"])
+        assert v.tolist() == call["values_out"] and i.tolist() == call["idx_out"] and rs.tolist() == call["row_splits_out"]
+    v, i, rs = nb.batch_top_k_on_rt(np.zeros(0, np.float32), np.array([0], np.int64), 3)
+    assert v.size == 0 and i.size == 0 and rs.tolist() == [0]
+    with pytest.raises(nb.NannError) as e:
+        nb.batch_top_k_on_rt(np.array(c["values"], np.float32), np.array(c["row_splits"], np.int64), [1, 2])
+    assert e.value.code == nb._lib.INVALID_ARGUMENT
+    rng = np.random.default_rng(12)                                              # a batch of queries' candidate lists
+    lens = rng.integers(0, 3000, 40)
+    rs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    vals = rng.integers(0, 200, rs[-1]).astype(np.float32)                        # ties
+    ks = rng.integers(0, 500, 40).astype(np.int64)
+    for asc in (False, True):
+        want = oracle.batch_top_k_on_rt(vals, rs, ks, asc)
+        got = nb.batch_top_k_on_rt(vals, rs, ks, asc)
+        for w, g in zip(want, got):
+            np.testing.assert_array_equal(g, w)

@@ -190,3 +190,14 @@ def test_search_error_when_fewer_than_k(oracle, small_world):
     T = [len(small_world["ep"]) + 1, 10, 10, 10, 10, 10]                 # topk_op.cc:66-69
     res = ix.search(lambda r, ids: m.score(u, small_world["emb"], ids), T)
     assert res["status"] == oracle.INVALID_ARGUMENT
+
+
+def test_batch_topk_on_rt_golden(oracle):
+    c = KAT["batch_topk_on_rt"]
+    for call in c["calls"]:
+        v, i, rs = oracle.batch_top_k_on_rt(c["values"], c["row_splits"], call["k"], call["ascending"])
+        assert v.tolist() == call["values_out"] and i.tolist() == call["idx_out"] and rs.tolist() == call["row_splits_out"]
+    v, i, rs = oracle.batch_top_k_on_rt(c["void"]["values"], c["void"]["row_splits"], c["void"]["k"])
+    assert v.size == 0 and i.size == 0 and rs.tolist() == [0]
+    with pytest.raises(oracle.OracleError):
+        oracle.batch_top_k_on_rt(c["values"], c["row_splits"], [1, 2])          # k vector length != groups

@@ -69,3 +69,36 @@ def test_scorer_id_range_check(nb, small_world):
     with pytest.raises(nb.NannError) as e:
         nb.score_ids(s, small_world["queries"][0], small_world["emb"][:100], np.array([1, 100], np.int32))
     assert e.value.code == nb._lib.INVALID_ARGUMENT
+
+
+@pytest.mark.parametrize("n", [2, 127, 128, 129, 1000, 14800, 60000])
+def test_mlp_tensor_core_within_tolerance(nb, oracle, small_world, n):
+    """NANN_SCORER_TENSOR (tcgen05, fp16 hi/lo split, fp32 accumulate): |score - oracle| <= 1e-5."""
+    emb = small_world["emb"]
+    m = oracle.Mlp(*small_world["mlp"])
+    s = nb.Scorer.mlp(*small_world["mlp"])
+    s.set_precision(nb.SCORER_TENSOR)
+    rng = np.random.default_rng(n)
+    ids = rng.integers(0, emb.shape[0], n).astype(np.int32)
+    u = small_world["queries"][n % 64]
+    want = m.score(u, emb, ids)
+    got = nb.score_ids(s, u, emb, ids)
+    assert not np.isnan(got).any()
+    assert np.abs(got - want).max() <= TOL
+    got2 = nb.blaze_xla_op(s, u, emb[ids])
+    assert np.abs(got2 - want).max() <= TOL
+    s.set_precision(nb.SCORER_EXACT)                     # switching back restores bit-exactness
+    np.testing.assert_array_equal(nb.score_ids(s, u, emb, ids).view(np.uint32), want.view(np.uint32))
+
+
+def test_mlp_tensor_core_larger_magnitudes(nb, oracle, small_world):
+    """inputs 30x larger than the synthetic corpus: the error bound is relative to the score scale."""
+    W1, b1, W2, b2, w3 = small_world["mlp"]
+    rng = np.random.default_rng(5)
+    x = (rng.standard_normal((2000, 128)) * 3).astype(np.float32)
+    u = (rng.standard_normal(128) * 3).astype(np.float32)
+    m = oracle.Mlp(W1, b1, W2, b2, w3)
+    s = nb.Scorer.mlp(W1, b1, W2, b2, w3)
+    s.set_precision(nb.SCORER_TENSOR)
+    want, got = m.score(u, x), nb.blaze_xla_op(s, u, x)
+    assert np.abs(got - want).max() <= 1e-5 * max(1.0, float(np.abs(want).max()))

@@ -218,3 +218,29 @@ def test_executor_closed_loop(nb, world):
     r3 = harness.run_benchmark(world["ix"], world["scorer"], T, world["queries"], predictor_num=1, bench_thread_count=1,
                                duration=1.0, qps=200, max_batch_size=8)
     assert 100 <= r3["throughput"] <= 260                                           # paced load is respected
+
+
+def test_tensor_core_scorer_search_parity(nb, oracle, world):
+    """TENSOR scorer: (1) every traced score within 1e-5 of the oracle's exact score, (2) the integer
+    traversal bit-exact GIVEN those scores, (3) the final top-k agrees with the exact path except
+    where two scores are closer than the tolerance."""
+    T = world["T"]
+    sc = nb.Scorer.mlp(*world["mlp"])
+    sc.set_precision(nb.SCORER_TENSOR)
+    s = nb.Searcher(world["ix"], sc, 16, T)
+    s.set_trace(True)
+    users = world["queries"][32:48]
+    got = s.search(users, T)
+    assert np.all(got["status"] == 0)
+    exact = _oracle_batch(world, users, T)
+    overlap = 0
+    for q in range(16):
+        traced = [s.trace(q, r) for r in range(5)]
+        for r in range(5):
+            want = world["omlp"].score(users[q], world["emb"], traced[r][0])
+            assert np.abs(want - traced[r][1]).max() <= 1e-5
+        ref = world["oix"].search(lambda r, ids, t=traced: t[r][1], T)
+        np.testing.assert_array_equal(got["ids"][q], ref["ids"])
+        np.testing.assert_array_equal(got["scores"][q].view(np.uint32), ref["scores"].view(np.uint32))
+        overlap += len(set(got["ids"][q].tolist()) & set(exact["ids"][q].tolist()))
+    assert overlap >= 0.99 * 16 * T[5]
