@@ -136,19 +136,24 @@ mlp_exact_kernel(MlpExactArgs p) {
   if (t0 >= n) return;
   const int nt = min(EX_TM, n - t0);
 
-  // ---- gather: warp w loads rows w, w+8, ...; one float4 per lane = one 512-B row per warp
+  // ---- gather: warp w owns rows w*8 .. w*8+7; one float4 per lane = one 512-B row per warp request;
+  // ids come from one coalesced load and all 8 row loads are in flight before the first store
   {
     const int warp = tid >> 5, lane = tid & 31;
-    for (int c = warp; c < EX_TM; c += EX_THREADS / 32) {
-      const int cc = c < nt ? c : 0;  // pad with the tile's first row (scores not written)
-      const float* src;
-      if (p.ids) src = p.table + (int64_t)p.ids[(int64_t)q * p.ids_stride + t0 + cc] * MLP_D;
-      else       src = p.table + ((int64_t)q * p.rows_stride + t0 + cc) * MLP_D;
-      float4 v;
-      asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-                   : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(src + lane * 4));
-      *reinterpret_cast<float4*>(xs + c * EX_XP + lane * 4) = v;
+    const int my_r = warp * 8 + (lane & 7);
+    const int my_cc = my_r < nt ? my_r : 0;   // pad with the tile's first row (scores not written)
+    const long long my_row_idx = p.ids ? (long long)p.ids[(int64_t)q * p.ids_stride + t0 + my_cc]
+                                       : ((long long)q * p.rows_stride + t0 + my_cc);
+    float4 v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const long long ridx = __shfl_sync(0xffffffffu, my_row_idx, j);
+      const float* src = p.table + ridx * MLP_D + lane * 4;
+      asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+          : "=f"(v[j].x), "=f"(v[j].y), "=f"(v[j].z), "=f"(v[j].w) : "l"(src));
     }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(xs + (warp * 8 + j) * EX_XP + lane * 4) = v[j];
   }
   __syncthreads();
 

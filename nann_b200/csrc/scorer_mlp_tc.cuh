@@ -98,6 +98,14 @@ __host__ __device__ __forceinline__ uint32_t sw128_chunk_off(int r, int c) {
   return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
 }
 
+// 16-byte streaming load of a table row chunk; NOT volatile so several can be put in flight
+__device__ __forceinline__ float4 ld_row16(const float* p) {
+  float4 v;
+  asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+      : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
 __device__ __forceinline__ void split_f16(float a, __half& hi, __half& lo) {
   hi = __float2half_rn(a);
   lo = __float2half_rn(a - __half2float(hi));
@@ -162,24 +170,35 @@ mlp_tc_kernel(MlpTcArgs p) {
     const int nt = min(TC_M, n - t0);
 
     // ---- gather + split: x tile -> sA as [plane][slab][128 rows x 128 B swizzled]
-    for (int c = warp; c < TC_M; c += TC_THREADS / 32) {
-      const int cc = c < nt ? c : 0;
-      const float* src = p.ids ? p.table + (int64_t)p.ids[(int64_t)q * p.ids_stride + t0 + cc] * MLP_D
-                               : p.table + ((int64_t)q * p.rows_stride + t0 + cc) * MLP_D;
-      float4 v;
-      asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-                   : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(src + lane * 4));
-      __half h[4], l[4];
-      split_f16(v.x, h[0], l[0]); split_f16(v.y, h[1], l[1]);
-      split_f16(v.z, h[2], l[2]); split_f16(v.w, h[3], l[3]);
-      const int k = lane * 4, slab = k >> 6, chunk = (k & 63) >> 3, sub = (k & 7) * 2;
-      const uint32_t off = slab * TC_SLAB_BYTES + sw128_chunk_off(c, chunk) + sub;
-      *reinterpret_cast<uint2*>(sA + off) = make_uint2(
-          (uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16),
-          (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16));
-      *reinterpret_cast<uint2*>(sA + 2 * TC_SLAB_BYTES + off) = make_uint2(
-          (uint32_t)__half_as_ushort(l[0]) | ((uint32_t)__half_as_ushort(l[1]) << 16),
-          (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16));
+    {  // warp w owns rows w*16 .. w*16+15: coalesced id load, 8 row loads in flight at a time
+      const int my_r = warp * 16 + (lane & 15);
+      const int my_cc = my_r < nt ? my_r : 0;
+      const long long my_row_idx = p.ids ? (long long)p.ids[(int64_t)q * p.ids_stride + t0 + my_cc]
+                                         : ((long long)q * p.rows_stride + t0 + my_cc);
+#pragma unroll 1
+      for (int i0 = 0; i0 < 16; i0 += 8) {
+        float4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const long long ridx = __shfl_sync(0xffffffffu, my_row_idx, i0 + j);
+          v[j] = ld_row16(p.table + ridx * MLP_D + lane * 4);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int c = warp * 16 + i0 + j;
+          __half h[4], l[4];
+          split_f16(v[j].x, h[0], l[0]); split_f16(v[j].y, h[1], l[1]);
+          split_f16(v[j].z, h[2], l[2]); split_f16(v[j].w, h[3], l[3]);
+          const int k = lane * 4, slab = k >> 6, chunk = (k & 63) >> 3, sub = (k & 7) * 2;
+          const uint32_t off = slab * TC_SLAB_BYTES + sw128_chunk_off(c, chunk) + sub;
+          *reinterpret_cast<uint2*>(sA + off) = make_uint2(
+              (uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16),
+              (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16));
+          *reinterpret_cast<uint2*>(sA + 2 * TC_SLAB_BYTES + off) = make_uint2(
+              (uint32_t)__half_as_ushort(l[0]) | ((uint32_t)__half_as_ushort(l[1]) << 16),
+              (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16));
+        }
+      }
     }
 
     // ================================ phase 1: layer 1 ========================================

@@ -232,24 +232,37 @@ mlp_tc2_kernel(MlpTcArgs p) {
       int q, t0, nt;
       if (!tile_info(g, q, t0, nt)) continue;
       // ---- gather + split (the previous tile's MMAs are complete: this thread waited on d2_full)
-      for (int c = ew; c < TC_M; c += 4) {
-        const int cc = c < nt ? c : 0;
-        const float* src = p.ids ? p.table + (int64_t)p.ids[(int64_t)q * p.ids_stride + t0 + cc] * MLP_D
-                                 : p.table + ((int64_t)q * p.rows_stride + t0 + cc) * MLP_D;
-        float4 v;
-        asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-                     : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(src + lane * 4));
-        __half h[4], l[4];
-        split_f16(v.x, h[0], l[0]); split_f16(v.y, h[1], l[1]);
-        split_f16(v.z, h[2], l[2]); split_f16(v.w, h[3], l[3]);
-        const int k = lane * 4, slab = k >> 6, chunk = (k & 63) >> 3, sub = (k & 7) * 2;
-        const uint32_t off = slab * TC_SLAB_BYTES + sw128_chunk_off(c, chunk) + sub;
-        *reinterpret_cast<uint2*>(sX + off) = make_uint2(
-            (uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16),
-            (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16));
-        *reinterpret_cast<uint2*>(sX + 2 * TC_SLAB_BYTES + off) = make_uint2(
-            (uint32_t)__half_as_ushort(l[0]) | ((uint32_t)__half_as_ushort(l[1]) << 16),
-            (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16));
+      // warp ew owns rows ew*32 .. ew*32+31: one coalesced id load, then row loads 8 at a time in
+      // flight (a row = one 512-B warp request) before any of them is consumed
+      {
+        const int my_r = ew * 32 + lane;
+        const int my_cc = my_r < nt ? my_r : 0;      // pad with the tile's first row (scores not written)
+        const long long my_row_idx = p.ids ? (long long)p.ids[(int64_t)q * p.ids_stride + t0 + my_cc]
+                                           : ((long long)q * p.rows_stride + t0 + my_cc);
+#pragma unroll 1
+        for (int i0 = 0; i0 < 32; i0 += 8) {
+          float4 v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const long long ridx = __shfl_sync(0xffffffffu, my_row_idx, i0 + j);
+            v[j] = ld_row16(p.table + ridx * MLP_D + lane * 4);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int c = ew * 32 + i0 + j;
+            __half h[4], l[4];
+            split_f16(v[j].x, h[0], l[0]); split_f16(v[j].y, h[1], l[1]);
+            split_f16(v[j].z, h[2], l[2]); split_f16(v[j].w, h[3], l[3]);
+            const int k = lane * 4, slab = k >> 6, chunk = (k & 63) >> 3, sub = (k & 7) * 2;
+            const uint32_t off = slab * TC_SLAB_BYTES + sw128_chunk_off(c, chunk) + sub;
+            *reinterpret_cast<uint2*>(sX + off) = make_uint2(
+                (uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16),
+                (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16));
+            *reinterpret_cast<uint2*>(sX + 2 * TC_SLAB_BYTES + off) = make_uint2(
+                (uint32_t)__half_as_ushort(l[0]) | ((uint32_t)__half_as_ushort(l[1]) << 16),
+                (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16));
+          }
+        }
       }
       fence_proxy_async();
       mbar_arrive(B(T2Bars::x_ready));

@@ -78,15 +78,25 @@ expand_filter_kernel(const int32_t* __restrict__ nbr_vals, const int64_t* __rest
   const int32_t* fr = frontier + (int64_t)q * f_stride;
   int64_t o = 0, expanded = 0;
   int bad = 0;
-  for (int base = 0; base < f_n; base += 32) {
+  // Software pipeline (all of it latency-bound pointer chasing): the CSR row bounds of the NEXT
+  // 32 frontier nodes and the neighbour ids of the NEXT 32-id step are requested before the
+  // current step's bitmap round trip, so each step exposes one L2 latency instead of three.
+  auto load_rows = [&](int base, long long& s, int& len) {
     const int fi = base + (int)lane;
-    long long s = 0;
-    int len = 0;
+    s = 0; len = 0;
     if (fi < f_n) {
       const int32_t node = fr[fi];
       s = nbr_rs[node];
       len = (int)(nbr_rs[node + 1] - s);
     }
+  };
+  long long s_nx = 0;
+  int len_nx = 0;
+  load_rows(0, s_nx, len_nx);
+  for (int base = 0; base < f_n; base += 32) {
+    const long long s = s_nx;
+    const int len = len_nx;
+    if (base + 32 < f_n) load_rows(base + 32, s_nx, len_nx);
     int incl = len;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -95,9 +105,8 @@ expand_filter_kernel(const int32_t* __restrict__ nbr_vals, const int64_t* __rest
     }
     const int total = __shfl_sync(FULL, incl, 31);
     const int excl = incl - len;
-    for (int p0 = 0; p0 < total; p0 += 32) {
+    auto load_step = [&](int p0) -> int32_t {
       const int p = p0 + (int)lane;
-      const bool valid = p < total;
       int j = 0;  // owner = last lane whose exclusive offset is <= p
 #pragma unroll
       for (int step = 16; step > 0; step >>= 1) {
@@ -107,7 +116,13 @@ expand_filter_kernel(const int32_t* __restrict__ nbr_vals, const int64_t* __rest
       }
       const long long sj = __shfl_sync(FULL, s, j);
       const int ej = __shfl_sync(FULL, excl, j);
-      int32_t v = valid ? nbr_vals[sj + (p - ej)] : -1;
+      return p < total ? nbr_vals[sj + (p - ej)] : -1;
+    };
+    int32_t v_nx = total > 0 ? load_step(0) : -1;
+    for (int p0 = 0; p0 < total; p0 += 32) {
+      const int32_t v = v_nx;
+      if (p0 + 32 < total) v_nx = load_step(p0 + 32);
+      const bool valid = p0 + (int)lane < total;
       o += filter_step<int32_t>(v, valid, bm, n_words, out, o, &bad);
     }
     expanded += total;
