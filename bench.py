@@ -259,11 +259,11 @@ def run_b200(args, T, rank, world, local_rank):
         extra["recall_error"] = repr(e)[:200]
 
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:   # cpu_baseline: rank 0 at N=1 only
         try:
             from oracle import oracle as orc
             cores = os.cpu_count() or 1
-            sh1 = sh if world == 1 else get_shard(args.n_items, 1, 0, dev)
+            sh1 = sh
             oix = orc.Index(sh1["emb"], sh1["item_ids"], sh1["ep"].astype(np.int32), [v.astype(np.int32) for v in sh1["values"]], sh1["row_splits"])
             om = orc.Mlp(*sw.mlp_weights(seed=3))
             sample_q = args.cpu_sample or int(min(B, max(32, 4 * cores)))

@@ -104,7 +104,9 @@ static nann_status ids_to_device_i32(const void* src, int dtype, int64_t n, int6
 }
 
 // ---- scorer dispatch ------------------------------------------------------------------------
+struct TcWorkspace;
 struct ScoreCall {
+  TcWorkspace* ws = nullptr;   // tensor-core path scratch, owned by the caller (one per stream)
   const float* table; const int32_t* ids; int64_t ids_stride; int64_t rows_stride;
   const int32_t* n_ptr; int n_fixed; int max_n; int B;
   const float* hu;      // mlp: hoisted layer-1 prefix [B][H];  attention: key side [B][50][256]
@@ -249,9 +251,14 @@ static nann_status scorer_run_common(nann_scorer_t* s, const float* user, const 
   c.table = d_tab.d; c.ids = d_ids.d; c.ids_stride = 0; c.rows_stride = 0;
   c.n_ptr = nullptr; c.n_fixed = (int)n; c.max_n = (int)n; c.B = 1;
   c.hu = hu.d; c.users = d_user.d; c.out = d_out.d; c.out_stride = 0; c.status = nullptr;
-  NANN_TRY(scorer_score(s, c, st));
-  NANN_TRY(d_out.finish(st));
-  NANN_CUDA(cudaStreamSynchronize(st));
+  TcWorkspace ws;   // op-level call: private scratch for the duration of the call
+  c.ws = &ws;
+  nann_status rc_score = scorer_score(s, c, st);
+  if (rc_score == NANN_OK) rc_score = d_out.finish(st);
+  cudaError_t sync_err = cudaStreamSynchronize(st);
+  tc_ws_free(&ws);
+  NANN_TRY(rc_score);
+  NANN_CUDA(sync_err);
   return NANN_OK;
 }
 
@@ -404,6 +411,7 @@ struct nann_searcher {
   int32_t* res_ids = nullptr; float* res_sc = nullptr;     // [maxB][maxr]
   int32_t* out_nodes = nullptr; float* out_sc = nullptr; int64_t* out_item = nullptr;  // [maxB][T5]
   int32_t* status = nullptr;   // [maxB]
+  nann::TcWorkspace* tcws = nullptr;                        // tensor-core scorer scratch (lazy)
   bool trace = false;
   int32_t* tr_ids = nullptr; float* tr_sc = nullptr;       // [5][maxB][maxc] when tracing
   // host mirrors of the last call
@@ -428,6 +436,7 @@ void nann_searcher_destroy(nann_searcher_t* s) {
   cudaFree(s->res_ids); cudaFree(s->res_sc); cudaFree(s->out_nodes); cudaFree(s->out_sc);
   cudaFree(s->out_item); cudaFree(s->status); cudaFree(s->tr_ids); cudaFree(s->tr_sc);
   for (auto e : s->ev) cudaEventDestroy(e);
+  if (s->tcws) { nann::tc_ws_free(s->tcws); delete s->tcws; }
   delete s;
 }
 
@@ -547,6 +556,8 @@ nann_status nann_search_batch(nann_searcher_t* s, const float* users, int B, con
     c.table = ix->emb; c.ids = ids; c.ids_stride = ids_stride; c.rows_stride = 0;
     c.n_ptr = n_ptr; c.n_fixed = n_fixed; c.max_n = (int)std::min<int64_t>(bound, s->maxc); c.B = B;
     c.hu = s->ustate; c.users = s->users; c.out = s->cand_sc; c.out_stride = s->maxc; c.status = s->status;
+    if (!s->tcws) s->tcws = new nann::TcWorkspace();
+    c.ws = s->tcws;
     t_begin(0);
     nann_status rc_score = scorer_score(s->sc, c, st);
     t_end();

@@ -1,61 +1,70 @@
-// scorer_mlp_tc2.cuh -- warp-specialised version of the tcgen05 scorer (same math, same weight
-// images, same L2 scratch as scorer_mlp_tc.cuh; see that file for the numerics).
-//
-// Roles inside one persistent CTA (320 threads, 1 CTA / SM):
-//   warp 0   producer: one thread streams 32-KB operand stages with cp.async.bulk (TMA 1-D bulk copy)
-//            into a 5-deep shared-memory ring, completion on mbarriers (complete_tx)
-//   warp 1   MMA issuer: one thread issues tcgen05.mma (kind::f16, M=128, N=128/256), releases ring
-//            slots and publishes accumulators with tcgen05.commit -> mbarrier
-//   warps 2-9 gather + epilogues: row gather/split into the x tile, TMEM -> registers epilogues
-//            (two warps per TMEM lane quarter, each taking half of the columns)
-// so loads, tensor-core math and epilogues of different stages overlap without any CTA-wide barrier.
-//
-// Shared memory: [x tile / phase-2 A double buffer 64 KB][ring 5 x 32 KB][barriers].
-// Stage stream per tile (each 32 KB, contiguous in the pre-swizzled images):
-//   phase 1, chunk c=0..3 :  W1hi(c) -> MMAs Xh*Bh, Xl*Bh ;  W1lo(c) -> MMAs Xh*Bl      (N=128)
-//   phase 2, slab  s=0..7 :  A(s) = h1 slab from the L2 scratch (hi 16 KB + lo 16 KB), then for
-//                            h=0,1: W2hi(s,h) -> Ah*Bh, Al*Bh ; W2lo(s,h) -> Ah*Bl        (N=256)
+// scorer_mlp_tc3.cuh -- scorer_mlp_tc2.cuh's warp-specialised tcgen05 kernel driven by a dense tile list
+// and, for CL = 2, launched as thread-block clusters whose CTAs share the weight stream: each CTA
+// fetches half of every 32-KB weight stage and TMA-multicasts it into both CTAs' rings
+// (cp.async.bulk ... .multicast::cluster), halving the L2->SM weight traffic that bounds the kernel;
+// ring slots are released by tcgen05.commit ... .multicast::cluster from both MMA threads.
+// GENERATED from scorer_mlp_tc2.cuh's kernel body by a mechanical edit; keep the two in sync.
 #pragma once
 
 namespace nann {
 
-constexpr int T2_EPI_WARPS = 8;                       // gather + epilogue warps: two per TMEM lane quarter
-constexpr int T2_EPI_THREADS = T2_EPI_WARPS * 32;
-constexpr int T2_THREADS = 64 + T2_EPI_THREADS;
-constexpr int T2_STAGE = 32768;
-constexpr int T2_NS = 5;
-constexpr int T2_X_BYTES = 65536;
-constexpr int T2_SMEM_BYTES = T2_X_BYTES + T2_NS * T2_STAGE + 1024 /*align*/ + 1024 /*barriers, tmem slot, partials*/;
-
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+               ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar), "h"(mask) : "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
 }
-// 1-D bulk copy global -> shared, completion counted on an mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
+
+// ---- tile list: tiles[g] = (q, t) for every 128-row tile of every live query ------------------------
+__global__ void __launch_bounds__(1024)
+tile_scan_kernel(const int32_t* __restrict__ n_ptr, int n_fixed, const int32_t* __restrict__ status, int B,
+                 int32_t* __restrict__ tile_start /* [B+1] */) {
+  __shared__ int warp_sum[32];
+  __shared__ int carry;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  if (tid == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < B; base += 1024) {
+    const int q = base + tid;
+    int c = 0;
+    if (q < B && !(status && status[q] != 0)) {
+      const int n = n_ptr ? n_ptr[q] : n_fixed;
+      c = n > 0 ? (n + TC_M - 1) / TC_M : 0;
+    }
+    int incl = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+    if (lane == 31) warp_sum[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+      int s = warp_sum[lane];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, s, d); if (lane >= d) s += t; }
+      warp_sum[lane] = s;
+    }
+    __syncthreads();
+    const int excl = carry + (w > 0 ? warp_sum[w - 1] : 0) + incl - c;
+    if (q < B) tile_start[q] = excl;
+    __syncthreads();
+    if (tid == 1023) carry = excl + c;
+    __syncthreads();
+  }
+  if (tid == 0) tile_start[B] = carry;
 }
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__global__ void tile_fill_kernel(const int32_t* __restrict__ tile_start, int B, int2* __restrict__ tiles) {
+  const int q = blockIdx.x;
+  const int s = tile_start[q], e = tile_start[q + 1];
+  for (int t = threadIdx.x; t < e - s; t += blockDim.x) tiles[s + t] = make_int2(q, t);
+}
 
-struct T2Bars {           // byte offsets inside the barrier block (8 B each)
-  static constexpr int full = 0;        // [5]
-  static constexpr int empty = 5;       // [5]
-  static constexpr int a_full = 10;     // [2]
-  static constexpr int a_empty = 12;    // [2]
-  static constexpr int x_ready = 14;
-  static constexpr int d1_full = 15;    // [2]
-  static constexpr int d1_empty = 17;   // [2]
-  static constexpr int h1_done = 19;    // [4]
-  static constexpr int d2_full = 23;
-  static constexpr int d2_empty = 24;
-  static constexpr int count = 25;
-};
-
+template <int CL>
 __global__ void __launch_bounds__(T2_THREADS, 1)
-mlp_tc2_kernel(MlpTcArgs p) {
+mlp_tc3_kernel(MlpTcArgs p) {
+  // cluster rank / peers (CL == 1: a plain launch, rank 0)
+  uint32_t cta_rank = 0;
+  if (CL > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sX = smem;                                   // x tile, later A double buffer (2 x 32 KB)
@@ -69,7 +78,7 @@ mlp_tc2_kernel(MlpTcArgs p) {
   auto B = [&](int idx) { return bar0 + 8u * (uint32_t)idx; };
 
   if (tid == 0) {
-    for (int i = 0; i < T2_NS; ++i) { mbar_init(B(T2Bars::full + i), 1); mbar_init(B(T2Bars::empty + i), 1); }
+    for (int i = 0; i < T2_NS; ++i) { mbar_init(B(T2Bars::full + i), 1); mbar_init(B(T2Bars::empty + i), CL); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(B(T2Bars::a_full + i), 1); mbar_init(B(T2Bars::a_empty + i), 1);
       mbar_init(B(T2Bars::d1_full + i), 1); mbar_init(B(T2Bars::d1_empty + i), T2_EPI_THREADS);
@@ -86,20 +95,26 @@ mlp_tc2_kernel(MlpTcArgs p) {
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) {   // peers' barriers must be initialised before any remote arrive / multicast lands
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t sX_u = smem_u32(sX), sR_u = smem_u32(sR);
   uint8_t* scratch = p.scratch + (size_t)blockIdx.x * TC_SCRATCH_BYTES;
-  const int64_t n_tiles = (int64_t)p.B * p.tiles_per_q;
-
-  // every role walks the same tile sequence and skips the same tiles
+  // dense tile list built by tile_scan/tile_fill: tiles[g] = (query, tile index).  A cluster walks
+  // tile GROUPS of CL tiles so that its CTAs consume the multicast weight stream in lockstep; a CTA
+  // whose tile index is past the end runs a dummy tile (nt = 0, nothing written).
+  const int64_t total = *p.tile_total;
+  const int64_t n_tiles = (total + CL - 1) / CL * CL;
+  const int64_t g_first = (int64_t)(blockIdx.x / CL) * CL + cta_rank, g_step = (int64_t)(gridDim.x / CL) * CL;
   auto tile_info = [&](int64_t g, int& q, int& t0, int& nt) -> bool {
-    q = (int)(g / p.tiles_per_q);
-    const int t = (int)(g % p.tiles_per_q);
-    if (p.status && p.status[q] != 0) return false;
+    if (g >= total) { q = p.tiles[0].x; t0 = 0; nt = 0; return true; }
+    const int2 e = p.tiles[g];
+    q = e.x;
     const int n = p.n_ptr ? p.n_ptr[q] : p.n_fixed;
-    t0 = t * TC_M;
-    if (t0 >= n) return false;
+    t0 = e.y * TC_M;
     nt = min(TC_M, n - t0);
     return true;
   };
@@ -112,12 +127,18 @@ mlp_tc2_kernel(MlpTcArgs p) {
       uint32_t h1_ph = 0;                      // parity of h1_done[*] (one completion per tile each)
       auto ring_load = [&](const void* src) {
         const uint32_t slot = it % T2_NS, ph = (it / T2_NS) & 1;
-        mbar_wait(B(T2Bars::empty + slot), ph ^ 1);
+        mbar_wait(B(T2Bars::empty + slot), ph ^ 1);          // released by the MMA threads of ALL CTAs of the cluster
         mbar_expect_tx(B(T2Bars::full + slot), T2_STAGE);
-        bulk_g2s(sR_u + slot * T2_STAGE, src, T2_STAGE, B(T2Bars::full + slot));
+        if (CL == 1) {
+          bulk_g2s(sR_u + slot * T2_STAGE, src, T2_STAGE, B(T2Bars::full + slot));
+        } else {   // this CTA fetches 1/CL of the stage and multicasts it into every CTA of the cluster
+          constexpr uint32_t part_bytes = T2_STAGE / CL;
+          bulk_g2s_mc(sR_u + slot * T2_STAGE + cta_rank * part_bytes, (const uint8_t*)src + cta_rank * part_bytes,
+                      part_bytes, B(T2Bars::full + slot), (uint16_t)((1u << CL) - 1));
+        }
         ++it;
       };
-      for (int64_t g = blockIdx.x; g < n_tiles; g += gridDim.x) {
+      for (int64_t g = g_first; g < n_tiles; g += g_step) {
         int q, t0, nt;
         if (!tile_info(g, q, t0, nt)) continue;
         for (int c = 0; c < 4; ++c) {
@@ -151,8 +172,12 @@ mlp_tc2_kernel(MlpTcArgs p) {
         tc_fence_after();
         return sR_u + slot * T2_STAGE;
       };
-      auto ring_release = [&]() { tc_commit(B(T2Bars::empty + (it % T2_NS))); ++it; };
-      for (int64_t g = blockIdx.x; g < n_tiles; g += gridDim.x) {
+      auto ring_release = [&]() {
+        if (CL == 1) tc_commit(B(T2Bars::empty + (it % T2_NS)));
+        else tc_commit_mc(B(T2Bars::empty + (it % T2_NS)), (uint16_t)((1u << CL) - 1));
+        ++it;
+      };
+      for (int64_t g = g_first; g < n_tiles; g += g_step) {
         int q, t0, nt;
         if (!tile_info(g, q, t0, nt)) continue;
         mbar_wait(B(T2Bars::d2_empty), d2e_ph); d2e_ph ^= 1;      // previous tile's epilogue drained TMEM
@@ -238,7 +263,7 @@ mlp_tc2_kernel(MlpTcArgs p) {
       const int cc = r < nt ? r : 0;          // pad with the tile's first row (scores not written)
       return p.ids ? (long long)p.ids[(int64_t)q * p.ids_stride + t0 + cc] : ((long long)q * p.rows_stride + t0 + cc);
     };
-    for (int64_t g = blockIdx.x; g < n_tiles; g += gridDim.x) {
+    for (int64_t g = g_first; g < n_tiles; g += g_step) {
       int q, t0, nt;
       if (!tile_info(g, q, t0, nt)) continue;
       // ---- gather + split (the previous tile's MMAs are complete: this thread waited on d2_full).
@@ -276,10 +301,10 @@ mlp_tc2_kernel(MlpTcArgs p) {
 
       // ---- while this tile computes: pull the NEXT tile's rows towards L2 (4 x 128-B lines per row)
       {
-        int64_t g2 = g + gridDim.x;
+        const int64_t g2 = g + g_step;
         int q2 = 0, t02 = 0, nt2 = 0;
-        while (g2 < n_tiles && !tile_info(g2, q2, t02, nt2)) g2 += gridDim.x;
-        if (g2 < n_tiles && lane < ROWS_PER_WARP) {
+        if (g2 < total) tile_info(g2, q2, t02, nt2);
+        if (g2 < total && lane < ROWS_PER_WARP) {
           const float* r2 = p.table + row_index(q2, t02, nt2, ew * ROWS_PER_WARP + lane) * MLP_D;
 #pragma unroll
           for (int ln = 0; ln < 4; ++ln) asm volatile("prefetch.global.L2 [%0];" ::"l"(r2 + ln * 32));
@@ -353,6 +378,10 @@ mlp_tc2_kernel(MlpTcArgs p) {
   __syncwarp();
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) {   // no CTA may exit while a peer can still multicast into it or arrive on its barriers
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
 }
 
