@@ -72,15 +72,27 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Never hang the GPU: a wait that lasts longer than 2 s of wall clock (a lost arrival, i.e. a
+// pipeline bug) turns into a trap -> a CUDA error on the host instead of a dead device.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
+  unsigned long long t0 = 0;
   for (uint32_t spin = 0; !done; ++spin) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    if (spin > (1u << 24)) __trap();  // never hang the GPU: a lost arrival becomes an error
+    if (!done && (spin & 63) == 63) {
+      const unsigned long long now = global_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 2000000000ull) __trap();
+    }
   }
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
