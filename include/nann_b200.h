@@ -141,6 +141,37 @@ nann_status nann_batch_topk_on_rt_f32(const float* values_in, int64_t n_values, 
                                       int64_t n_row_splits, const int64_t* k, int64_t n_k, int ascending,
                                       nann_alloc_fn alloc, void* alloc_ctx, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Ragged-batch helpers (not in exec.pb; the reference's batch>1 plumbing).  T in {i32, i64}; outputs
+ * through the allocator callback: 0 = values (T), 1 = row_splits (i64).
+ *   BatchGatherOnRT  UO/beam_search_op/BatchGatherOnRT_kernel.cc:17-97: ret[j] = params[params_rs[g] + idx[j]]
+ *   BatchConcatOnRT  UO/beam_search_op/BatchConcatOnRT_kernel.cc:18-115: group g = left[g] ++ right[g]
+ *   SplitsGather     UO/beam_search_op/SplitsGather_kernel.cc:20-105: ranges [splits[i], splits[i+1]) expanded
+ *   BitmapInit       UO/bitmap_op/bitmap_ops.cc:28-75: bitmap[length] with the bits of idx set
+ *   BitmapDifference UO/bitmap_op/bitmap_ops.cc:83-143: like BitmapRefDifference on ONE list, but the flags
+ *                    are copied (idx_flag -> idx_flag_new) instead of mutated; output 0 = idx_next_new
+ * Error behaviour as the reference's (InvalidArgument on ragged validation / mismatching row_splits;
+ * void inputs -> [], [0]).
+ * ---------------------------------------------------------------------------------------- */
+#define NANN_RAGGED_DECL(T, SFX)                                                                                       \
+  nann_status nann_batch_gather_on_rt_##SFX(const T* params_values, int64_t n_pv, const int64_t* params_row_splits,      \
+                                            int64_t n_prs, const int64_t* indices_values, int64_t n_iv,                  \
+                                            const int64_t* indices_row_splits, int64_t n_irs, nann_alloc_fn alloc,       \
+                                            void* alloc_ctx, void* stream);                                              \
+  nann_status nann_batch_concat_on_rt_##SFX(const T* left_values, int64_t n_lv, const int64_t* left_row_splits,          \
+                                            int64_t n_lrs, const T* right_values, int64_t n_rv,                          \
+                                            const int64_t* right_row_splits, int64_t n_rrs, nann_alloc_fn alloc,         \
+                                            void* alloc_ctx, void* stream);                                              \
+  nann_status nann_splits_gather_##SFX(const T* splits, int64_t n_splits, const int64_t* indices_values, int64_t n_iv,   \
+                                       const int64_t* indices_row_splits, int64_t n_irs, nann_alloc_fn alloc,            \
+                                       void* alloc_ctx, void* stream);                                                   \
+  nann_status nann_bitmap_init_##SFX(const T* idx, int64_t n, int32_t length, int32_t* bitmap, void* stream);            \
+  nann_status nann_bitmap_difference_##SFX(const T* idx_next, int64_t n, const int32_t* idx_flag, int64_t n_flags,       \
+                                           int32_t* idx_flag_new, nann_alloc_fn alloc, void* alloc_ctx, void* stream);
+NANN_RAGGED_DECL(int32_t, i32)
+NANN_RAGGED_DECL(int64_t, i64)
+#undef NANN_RAGGED_DECL
+
 /* GatherV2 on axis 0: out[i] = table[ids[i]], row_bytes per row (build_opt_graph.py:92,144).
  * InvalidArgument when an id is outside [0, n_rows). */
 nann_status nann_gather_rows(const void* table, int64_t n_rows, int64_t row_bytes,

@@ -15,5 +15,6 @@
 
 #include "lib_core.inl"
 #include "lib_ops.inl"
+#include "lib_ragged.inl"
 #include "lib_search.inl"
 #include "lib_executor.inl"

@@ -135,6 +135,75 @@ def batch_top_k_on_rt(values_in, row_splits_in, k, ascending=False, stream=None)
     return (out.arrays.get(0, np.empty(0, np.float32)), out.arrays.get(1, np.empty(0, np.int64)), out.arrays[2])
 
 
+def _ragged2(fn32, fn64, a_vals, a_rs, b_vals, b_rs, b_dtype, stream):
+    dt = np.dtype(a_vals.dtype if not _is_torch(a_vals) else str(a_vals.dtype).split(".")[-1])
+    if dt not in (np.dtype("int32"), np.dtype("int64")):
+        raise TypeError("T must be int32 or int64")
+    av, n_av, k0 = _as(a_vals, dt)
+    ars, n_ars, k1 = _as(a_rs, np.int64)
+    bv, n_bv, k2 = _as(b_vals, b_dtype or dt)
+    brs, n_brs, k3 = _as(b_rs, np.int64)
+    out = _Outputs({0: dt, 1: np.int64})
+    L = _lib.lib()
+    fn = getattr(L, fn32 if dt == np.int32 else fn64)
+    fn.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                   _lib.ALLOC_FN, C.c_void_p, C.c_void_p]
+    check(fn(av, n_av, ars, n_ars, bv, n_bv, brs, n_brs, out.fn, None, _stream_ptr(stream)))
+    return out.arrays.get(0, np.empty(0, dt)), out.arrays[1]
+
+
+def batch_gather_on_rt(params_values, params_row_splits, indices_values, indices_row_splits, stream=None):
+    """tf.batch_gather_on_rt (BatchGatherOnRT_kernel.cc:17-40): per group, params[group][local index]."""
+    return _ragged2("nann_batch_gather_on_rt_i32", "nann_batch_gather_on_rt_i64", params_values, params_row_splits,
+                    indices_values, indices_row_splits, np.int64, stream)
+
+
+def batch_concat_on_rt(left_values, left_row_splits, right_values, right_row_splits, stream=None):
+    """tf.batch_concat_on_rt (BatchConcatOnRT_kernel.cc:18-39): group-wise concatenation of two ragged tensors."""
+    return _ragged2("nann_batch_concat_on_rt_i32", "nann_batch_concat_on_rt_i64", left_values, left_row_splits,
+                    right_values, right_row_splits, None, stream)
+
+
+def splits_gather(splits, indices_values, indices_row_splits, stream=None):
+    """tf.splits_gather (SplitsGather_kernel.cc:20-31): expands ranges [splits[i], splits[i+1]) per group."""
+    dt = np.dtype(splits.dtype if not _is_torch(splits) else str(splits.dtype).split(".")[-1])
+    sp, n_sp, k0 = _as(splits, dt)
+    iv, n_iv, k1 = _as(indices_values, np.int64)
+    irs, n_irs, k2 = _as(indices_row_splits, np.int64)
+    out = _Outputs({0: dt, 1: np.int64})
+    L = _lib.lib()
+    fn = L.nann_splits_gather_i32 if dt == np.int32 else L.nann_splits_gather_i64
+    fn.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, _lib.ALLOC_FN, C.c_void_p, C.c_void_p]
+    check(fn(sp, n_sp, iv, n_iv, irs, n_irs, out.fn, None, _stream_ptr(stream)))
+    return out.arrays.get(0, np.empty(0, dt)), out.arrays[1]
+
+
+def bitmap_init(idx, length, stream=None):
+    """tf.bitmap_init (bitmap_ops.cc:28-43): int32 bitmap of `length` words with the bits of idx set."""
+    dt = np.dtype(idx.dtype if not _is_torch(idx) else str(idx.dtype).split(".")[-1])
+    v, n, k0 = _as(idx, dt)
+    out = np.empty(max(int(length), 0), np.int32)
+    L = _lib.lib()
+    fn = L.nann_bitmap_init_i32 if dt == np.int32 else L.nann_bitmap_init_i64
+    fn.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]
+    check(fn(v, n, int(length), C.c_void_p(out.ctypes.data), _stream_ptr(stream)))
+    return out
+
+
+def bitmap_difference(idx_next, idx_flag, stream=None):
+    """tf.bitmap_difference (bitmap_ops.cc:83-96): returns (idx_next_new, idx_flag_new); idx_flag is NOT mutated."""
+    dt = np.dtype(idx_next.dtype if not _is_torch(idx_next) else str(idx_next.dtype).split(".")[-1])
+    v, n, k0 = _as(idx_next, dt)
+    fl, n_fl, k1 = _as(idx_flag, np.int32)
+    new = np.empty(n_fl, np.int32)
+    out = _Outputs({0: dt, 1: np.int64})
+    L = _lib.lib()
+    fn = L.nann_bitmap_difference_i32 if dt == np.int32 else L.nann_bitmap_difference_i64
+    fn.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, _lib.ALLOC_FN, C.c_void_p, C.c_void_p]
+    check(fn(v, n, fl, n_fl, C.c_void_p(new.ctypes.data), out.fn, None, _stream_ptr(stream)))
+    return out.arrays.get(0, np.empty(0, dt)), new
+
+
 def gather(params, indices, stream=None):
     """tf.gather(params, indices) on axis 0 (GatherV2) for a row-major table."""
     idx, n, k0 = _as(indices, np.int32)

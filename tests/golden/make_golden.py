@@ -117,6 +117,16 @@ kat = {
         ],
         "void": {"values": [], "row_splits": [0], "k": 3, "values_out": [], "idx_out": [], "row_splits_out": [0]},
     },
+    # "should be" comments of the reference's own scripts
+    "batch_gather_on_rt": {"source": "UO/beam_search_op/batch_gather_on_rt_test.py:17-35", "kind": "stated in reference comments",
+        "params_values": [1, 2, 3, 4, 5], "params_row_splits": [0, 3, 5], "indices_values": [0, 1, 1],
+        "indices_row_splits": [0, 2, 3], "ret_values": [1, 2, 5], "ret_row_splits": [0, 2, 3]},
+    "batch_concat_on_rt": {"source": "UO/beam_search_op/batch_concat_on_rt_test.py:13-35", "kind": "stated in reference comments",
+        "left_values": [1, 2, 3, 4, 5], "left_row_splits": [0, 3, 5], "right_values": [0, 1, 1], "right_row_splits": [0, 2, 3],
+        "ret_values": [1, 2, 3, 0, 1, 4, 5, 1], "ret_row_splits": [0, 5, 8]},
+    "splits_gather": {"source": "UO/beam_search_op/splits_gather_test.py:7-10,18-24", "kind": "stated in reference docstring",
+        "splits": [0, 2, 5, 7, 10], "indices_values": [0, 1, 3], "indices_row_splits": [0, 2, 3],
+        "ret_values": [0, 1, 2, 3, 4, 7, 8, 9], "ret_row_splits": [0, 5, 8]},
     # UO/huge_const_op/huge_const_test.py:6-27 -- arrays saved then read back through HugeConst
     "huge_const": [
         {"source": "UO/huge_const_op/huge_const_test.py:6,22,25", "dtype": "int32", "array": [[1, 2], [3, 4], [5, 6]]},

@@ -17,6 +17,9 @@ def _declared():
     src = open(HEADER).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     names = set(re.findall(r"\b(nann_[a-z0-9_]+)\s*\(", src))
+    for stem in re.findall(r"\b(nann_[a-z0-9_]+_)##SFX\s*\(", src):      # NANN_RAGGED_DECL(T, SFX) expansions
+        names |= {stem + "i32", stem + "i64"}
+    names = {n for n in names if not n.endswith("_")}
     names -= {"nann_alloc_fn"}
     return sorted(names)
 

@@ -239,3 +239,49 @@ def test_batch_topk_on_rt(nb, oracle):
         got = nb.batch_top_k_on_rt(vals, rs, ks, asc)
         for w, g in zip(want, got):
             np.testing.assert_array_equal(g, w)
+
+
+def test_ragged_batch_helpers(nb):
+    """BatchGatherOnRT / BatchConcatOnRT / SplitsGather / BitmapInit / BitmapDifference against the values the
+    reference's own scripts state ("should be ...") and against numpy restatements of the kernels."""
+    from nann_b200 import ops
+    i64 = lambda a: np.array(a, np.int64)
+    c = KAT["batch_gather_on_rt"]
+    v, rs = ops.batch_gather_on_rt(i64(c["params_values"]), i64(c["params_row_splits"]), i64(c["indices_values"]), i64(c["indices_row_splits"]))
+    assert v.tolist() == c["ret_values"] and rs.tolist() == c["ret_row_splits"]
+    for pv, prs, iv, irs in ((c["params_values"], c["params_row_splits"], [], [0]), ([], [0], c["indices_values"], c["indices_row_splits"]), ([], [0], [], [0])):
+        v, rs = ops.batch_gather_on_rt(i64(pv), i64(prs), i64(iv), i64(irs))     # "should be []"
+        assert v.size == 0 and rs.tolist() == [0]
+    with pytest.raises(nb.NannError):
+        ops.batch_gather_on_rt(i64([1, 2, 3]), i64([0, 3]), i64([0, 1, 1]), i64([0, 2, 3]))   # row_splits do NOT match
+    c = KAT["batch_concat_on_rt"]
+    v, rs = ops.batch_concat_on_rt(i64(c["left_values"]), i64(c["left_row_splits"]), i64(c["right_values"]), i64(c["right_row_splits"]))
+    assert v.tolist() == c["ret_values"] and rs.tolist() == c["ret_row_splits"]
+    v, rs = ops.batch_concat_on_rt(i64(c["left_values"]), i64(c["left_row_splits"]), i64([]), i64([0]))
+    assert v.tolist() == c["left_values"] and rs.tolist() == c["left_row_splits"]             # "should be [[1,2,3],[4,5]]"
+    v, rs = ops.batch_concat_on_rt(i64([]), i64([0]), i64(c["right_values"]), i64(c["right_row_splits"]))
+    assert v.tolist() == c["right_values"] and rs.tolist() == c["right_row_splits"]           # "should be [[0,1],[1]]"
+    c = KAT["splits_gather"]
+    v, rs = ops.splits_gather(i64(c["splits"]), i64(c["indices_values"]), i64(c["indices_row_splits"]))
+    assert v.tolist() == c["ret_values"] and rs.tolist() == c["ret_row_splits"]
+    v, rs = ops.splits_gather(i64([]), i64(c["indices_values"]), i64(c["indices_row_splits"]))
+    assert v.size == 0 and rs.tolist() == [0]
+    # random: numpy restatements
+    rng = np.random.default_rng(8)
+    lens = rng.integers(0, 50, 200); prs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    pv = rng.integers(0, 1000, prs[-1]).astype(np.int32)
+    ilen = np.where(lens > 0, rng.integers(0, 30, 200), 0); irs = np.concatenate([[0], np.cumsum(ilen)]).astype(np.int64)
+    iv = np.concatenate([rng.integers(0, max(l, 1), k) for l, k in zip(lens, ilen)]).astype(np.int64)
+    v, rs = ops.batch_gather_on_rt(pv, prs, iv, irs)
+    want = np.concatenate([pv[prs[g] + iv[irs[g]:irs[g + 1]]] for g in range(200)])
+    np.testing.assert_array_equal(v, want); np.testing.assert_array_equal(rs, irs)
+    rv = rng.integers(0, 1000, irs[-1]).astype(np.int32)
+    v, rs = ops.batch_concat_on_rt(pv, prs, rv, irs)
+    want = np.concatenate([np.concatenate([pv[prs[g]:prs[g + 1]], rv[irs[g]:irs[g + 1]]]) for g in range(200)])
+    np.testing.assert_array_equal(v, want); np.testing.assert_array_equal(rs, prs + irs)
+    bm = ops.bitmap_init(np.array([1, 2, 3, 4, 5, 6, 7, 8, 10, 11, 12, 13, 14], np.int32), 16)
+    assert bm.tolist()[:4] == [32254, 0, 0, 0]                                                # same bits as the chained KAT
+    flags = np.array([32254, 0, 0, 0], np.int32)
+    kept, new = ops.bitmap_difference(np.array([4, 9, 9, 40, 5, 127], np.int32), flags)
+    assert kept.tolist() == [9, 40, 127] and flags.tolist() == [32254, 0, 0, 0]              # value semantics: input untouched
+    assert new.view(np.uint32).tolist() == [32254 | (1 << 9), 1 << 8, 0, 1 << 31]
