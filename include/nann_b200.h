@@ -218,8 +218,8 @@ typedef struct nann_index nann_index_t;
 nann_status nann_index_create(int64_t n_items, int dim, const void* emb, int emb_dtype,
                               const int64_t* item_ids, const void* enter_points, int ep_dtype,
                               int64_t n_enter_points, const void* const nbr_values[2],
-                              int nbr_dtype, const int64_t* const nbr_row_splits[2], int device,
-                              nann_index_t** out);
+                              const int64_t n_nbr_values[2], int nbr_dtype,
+                              const int64_t* const nbr_row_splits[2], int device, nann_index_t** out);
 /* loads item_embs.npy, item_ids.npy from embs_dir and enter_points.npy,
  * neighbors_level_{0,1}_{values,row_splits}.npy from index_dir through nann_huge_const_create */
 nann_status nann_index_load(const char* embs_dir, const char* index_dir, int device,
@@ -265,6 +265,10 @@ nann_status nann_searcher_get_profile(nann_searcher_t* s, double stage_ms[4], in
                                       int64_t* rows_scored, int64_t* calls);
 /* node ids (rows of the table) of the last call's final top-k, [B][k], before the item_ids gather */
 nann_status nann_searcher_get_nodes(nann_searcher_t* s, int32_t* out_nodes, int64_t cap);
+
+/* debug: device buffer of 64*48 int64 that CTA 0 of the tensor-core scorer fills with clock64()
+ * stamps per (tile, pipeline event); NULL turns it off (scripts/tc_timeline.py) */
+nann_status nann_debug_tc_trace(long long* device_buffer_64x48);
 
 /* ------------------------------------------------------------------------------------------
  * Shard merge: G per-shard results [G][B][k_in] (score f32, id i64), as laid out by

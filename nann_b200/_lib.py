@@ -76,7 +76,7 @@ def lib():
     L.nann_scorer_destroy.argtypes = [vp]
     L.nann_blaze_xla_run.argtypes = [vp, vp, vp, i64, vp, vp]
     L.nann_scorer_run_ids.argtypes = [vp, vp, vp, i64, vp, i64, vp, vp]
-    L.nann_index_create.argtypes = [i64, i32, vp, i32, vp, vp, i32, i64, vp, i32, vp, i32, vp]
+    L.nann_index_create.argtypes = [i64, i32, vp, i32, vp, vp, i32, i64, vp, vp, i32, vp, i32, vp]
     L.nann_index_load.argtypes = [C.c_char_p, C.c_char_p, i32, vp]
     L.nann_index_n_items.restype = i64
     L.nann_index_n_items.argtypes = [vp]

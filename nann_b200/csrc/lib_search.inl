@@ -275,12 +275,12 @@ nann_status nann_scorer_run_ids(nann_scorer_t* s, const float* user, const float
 // ---- index -----------------------------------------------------------------------------------
 nann_status nann_index_create(int64_t n_items, int dim, const void* emb, int emb_dtype,
                               const int64_t* item_ids, const void* enter_points, int ep_dtype,
-                              int64_t n_ep, const void* const nbr_values[2], int nbr_dtype,
-                              const int64_t* const nbr_row_splits[2], int device, nann_index_t** out) {
+                              int64_t n_ep, const void* const nbr_values[2], const int64_t n_nbr_values[2],
+                              int nbr_dtype, const int64_t* const nbr_row_splits[2], int device, nann_index_t** out) {
   if (!out) return fail(NANN_INVALID_ARGUMENT, "null out");
   *out = nullptr;
   NANN_TRY(require_device());
-  if (n_items <= 0 || dim <= 0 || !emb || !item_ids || !enter_points || !nbr_values || !nbr_row_splits)
+  if (n_items <= 0 || dim <= 0 || !emb || !item_ids || !enter_points || !nbr_values || !n_nbr_values || !nbr_row_splits)
     return fail(NANN_INVALID_ARGUMENT, "nann_index_create: null or empty input");
   if (n_items > 0x7fffffffll) return fail(NANN_UNIMPLEMENTED, "n_items > 2^31-1 per shard");
   NANN_CUDA(cudaSetDevice(device));
@@ -312,7 +312,11 @@ nann_status nann_index_create(int64_t n_items, int dim, const void* emb, int emb
     int64_t nv = 0;
     if (cudaMemcpyAsync(&nv, ix->nbr_rs[l] + n_items, 8, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
         cudaStreamSynchronize(st) != cudaSuccess) { rc = fail(NANN_INTERNAL, "row_splits readback failed"); break; }
-    if (nv < 0) { rc = fail(NANN_INVALID_ARGUMENT, "row_splits[-1] < 0 at level %d", l); break; }
+    if (nv != n_nbr_values[l]) {   // ValidateRaggedTensor code 3 (GroupGather_kernel.cc:14)
+      rc = fail(NANN_INVALID_ARGUMENT, "Invalid RaggedTensor neighbors level %d, code: 3 (row_splits[-1]=%lld, %lld values)", l,
+                (long long)nv, (long long)n_nbr_values[l]);
+      break;
+    }
     ix->n_nbr[l] = nv;
     if (!step(ids_to_device_i32(nbr_values[l], nbr_dtype, nv, n_items, &ix->nbr_values[l], flags.d + 0, st))) break;
     NANN_LAUNCH(csr_check_kernel, (unsigned)std::min<int64_t>(ceil_div(n_items, 256), 1184), 256, 0, st, ix->nbr_rs[l], n_items,
@@ -371,9 +375,10 @@ nann_status nann_index_load(const char* embs_dir, const char* index_dir, int dev
   if (rc == NANN_OK) {
     const void* vals[2] = {nann_huge_const_host(h_v[0]), nann_huge_const_host(h_v[1])};
     const int64_t* rss[2] = {(const int64_t*)nann_huge_const_host(h_rs[0]), (const int64_t*)nann_huge_const_host(h_rs[1])};
+    const int64_t nvs[2] = {s_v[0].empty() ? 0 : s_v[0][0], s_v[1].empty() ? 0 : s_v[1][0]};
     rc = nann_index_create(s_emb[0], (int)s_emb[1], nann_huge_const_host(h_emb), dt_emb,
                            (const int64_t*)nann_huge_const_host(h_ids), nann_huge_const_host(h_ep), dt_ep, s_ep[0],
-                           vals, dt_v[0], rss, device, out);
+                           vals, nvs, dt_v[0], rss, device, out);
   }
   nann_huge_const_destroy(h_emb); nann_huge_const_destroy(h_ids); nann_huge_const_destroy(h_ep);
   for (int l = 0; l < 2; ++l) { nann_huge_const_destroy(h_v[l]); nann_huge_const_destroy(h_rs[l]); }

@@ -170,6 +170,7 @@ struct MlpTcArgs {
   uint8_t* scratch;       // [gridDim.x][TC_SCRATCH_BYTES]
   float* out; int64_t out_stride; const int32_t* status;
   const int2* tiles; const int32_t* tile_total;   // dense tile list (mlp_tc3_kernel)
+  long long* trace;                               // optional CTA-0 timeline [64 tiles][48 events] (debug)
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -448,6 +449,8 @@ static nann_status mlp_tc_prepare(nann_scorer* s) {
   return NANN_OK;
 }
 
+static long long* g_tc_trace = nullptr;   // set by nann_debug_tc_trace (debug builds of the timeline only)
+
 static nann_status mlp_tc_score(nann_scorer* s, const ScoreCall& c, cudaStream_t stm) {
   auto* st = (MlpTcState*)s->tc;
   if (!st) return fail(NANN_FAILED_PRECONDITION, "tensor-core scorer not prepared");
@@ -460,6 +463,7 @@ static nann_status mlp_tc_score(nann_scorer* s, const ScoreCall& c, cudaStream_t
   const int64_t n_tiles = (int64_t)a.B * a.tiles_per_q;
   NANN_TRY(tc_ws_ensure(c.ws, st->n_ctas, c.B, n_tiles));
   a.scratch = c.ws->scratch; a.tiles = c.ws->tiles; a.tile_total = c.ws->tile_start + c.B;
+  a.trace = g_tc_trace;
   // NANN_TC_KERNEL: 1 = bulk-synchronous cp.async kernel, 2 = warp-specialised TMA ring,
   // 3 = 2 + dense tile list, 4 (default) = 3 launched as 2-CTA clusters with multicast weight stages
   static const int version = [] { const char* e = std::getenv("NANN_TC_KERNEL"); return e ? atoi(e) : 4; }();
@@ -482,6 +486,13 @@ static nann_status mlp_tc_score(nann_scorer* s, const ScoreCall& c, cudaStream_t
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return NANN_OK;
 }
+
+}  // namespace nann
+extern "C" nann_status nann_debug_tc_trace(long long* device_buffer_64x48) {
+  nann::g_tc_trace = device_buffer_64x48;
+  return NANN_OK;
+}
+namespace nann {
 
 static void mlp_tc_release(nann_scorer* s) {
   auto* st = (MlpTcState*)s->tc;

@@ -65,6 +65,11 @@ mlp_tc3_kernel(MlpTcArgs p) {
   // cluster rank / peers (CL == 1: a plain launch, rank 0)
   uint32_t cta_rank = 0;
   if (CL > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+  // optional timeline of CTA 0 (debug): trace[tile][event] = clock64() ; see scripts/tc_timeline.py
+  long long* const trace = (blockIdx.x == 0) ? p.trace : nullptr;
+  auto TR = [&](int tile_local, int ev) {
+    if (trace && tile_local < 64) trace[tile_local * 48 + ev] = clock64();
+  };
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sX = smem;                                   // x tile, later A double buffer (2 x 32 KB)
@@ -138,17 +143,21 @@ mlp_tc3_kernel(MlpTcArgs p) {
         }
         ++it;
       };
+      int tl = -1;
       for (int64_t g = g_first; g < n_tiles; g += g_step) {
         int q, t0, nt;
         if (!tile_info(g, q, t0, nt)) continue;
+        ++tl;
         for (int c = 0; c < 4; ++c) {
+          if (c == 0) TR(tl, 32);
           ring_load((const uint8_t*)p.W1img + (size_t)c * TC_B_BYTES);
           ring_load((const uint8_t*)p.W1img + (size_t)c * TC_B_BYTES + T2_STAGE);
         }
         for (int s = 0; s < 8; ++s) {
-          if ((s & 1) == 0) mbar_wait(B(T2Bars::h1_done + (s >> 1)), h1_ph);   // epilogue of chunk s/2 wrote slabs s, s+1
+          if ((s & 1) == 0) { mbar_wait(B(T2Bars::h1_done + (s >> 1)), h1_ph); TR(tl, 28 + (s >> 1)); }   // epilogue of chunk s/2 wrote slabs s, s+1
           const int b = s & 1;
           mbar_wait(B(T2Bars::a_empty + b), a_cnt[b] & 1);                        // x tile / slab s-2 no longer read
+          TR(tl, 34 + s);
           mbar_expect_tx(B(T2Bars::a_full + b), T2_STAGE);
           bulk_g2s(sX_u + b * T2_STAGE, scratch + (size_t)s * T2_STAGE, T2_STAGE, B(T2Bars::a_full + b));
           ++a_cnt[b];
@@ -158,6 +167,7 @@ mlp_tc3_kernel(MlpTcArgs p) {
             ring_load(w + T2_STAGE);
           }
         }
+        TR(tl, 33);
         h1_ph ^= 1;
       }
     }
@@ -177,11 +187,15 @@ mlp_tc3_kernel(MlpTcArgs p) {
         else tc_commit_mc(B(T2Bars::empty + (it % T2_NS)), (uint16_t)((1u << CL) - 1));
         ++it;
       };
+      int tl = -1;
       for (int64_t g = g_first; g < n_tiles; g += g_step) {
         int q, t0, nt;
         if (!tile_info(g, q, t0, nt)) continue;
+        ++tl;
         mbar_wait(B(T2Bars::d2_empty), d2e_ph); d2e_ph ^= 1;      // previous tile's epilogue drained TMEM
+        TR(tl, 2);
         mbar_wait(B(T2Bars::x_ready), xr_ph); xr_ph ^= 1;         // x tile (hi/lo, swizzled) is in smem
+        TR(tl, 3);
         tc_fence_after();
         // ---- phase 1
         for (int c = 0; c < 4; ++c) {
@@ -212,6 +226,7 @@ mlp_tc3_kernel(MlpTcArgs p) {
             }
           ring_release();
           tc_commit(B(T2Bars::d1_full + b));
+          TR(tl, 4 + c);
         }
         tc_commit(B(T2Bars::a_empty + 0));      // x tile fully consumed: both A buffers may be overwritten
         tc_commit(B(T2Bars::a_empty + 1));
@@ -219,10 +234,12 @@ mlp_tc3_kernel(MlpTcArgs p) {
         mbar_wait(B(T2Bars::d1_empty + 0), (d1e_cnt[0] & 1) ^ 1);
         mbar_wait(B(T2Bars::d1_empty + 1), (d1e_cnt[1] & 1) ^ 1);
         tc_fence_after();
+        TR(tl, 16);
         // ---- phase 2
         for (int s = 0; s < 8; ++s) {
           const int b = s & 1;
           mbar_wait(B(T2Bars::a_full + b), a_cnt[b] & 1); ++a_cnt[b];
+          TR(tl, 17 + s);
           tc_fence_after();
           const uint32_t a_u = sX_u + b * T2_STAGE;               // [hi 16 KB][lo 16 KB]
           for (int h = 0; h < 2; ++h) {
@@ -249,6 +266,7 @@ mlp_tc3_kernel(MlpTcArgs p) {
           if (s < 6) tc_commit(B(T2Bars::a_empty + b));           // slab s consumed -> slab s+2 may load
         }
         tc_commit(B(T2Bars::d2_full));
+        TR(tl, 25);
       }
     }
   } else {
@@ -263,9 +281,13 @@ mlp_tc3_kernel(MlpTcArgs p) {
       const int cc = r < nt ? r : 0;          // pad with the tile's first row (scores not written)
       return p.ids ? (long long)p.ids[(int64_t)q * p.ids_stride + t0 + cc] : ((long long)q * p.rows_stride + t0 + cc);
     };
+    int tl = -1;
+    const bool tr_thread = (ew == 0 && lane == 0);
     for (int64_t g = g_first; g < n_tiles; g += g_step) {
       int q, t0, nt;
       if (!tile_info(g, q, t0, nt)) continue;
+      ++tl;
+      if (tr_thread) TR(tl, 0);
       // ---- gather + split (the previous tile's MMAs are complete: this thread waited on d2_full).
       // warp ew owns rows ew*16 .. +15: one coalesced id load, then row loads 8 at a time in flight
       // (a row = one 512-B warp request) before any of them is consumed.
@@ -298,6 +320,7 @@ mlp_tc3_kernel(MlpTcArgs p) {
       }
       fence_proxy_async();
       mbar_arrive(B(T2Bars::x_ready));
+      if (tr_thread) TR(tl, 1);
 
       // ---- while this tile computes: pull the NEXT tile's rows towards L2 (4 x 128-B lines per row)
       {
@@ -317,6 +340,7 @@ mlp_tc3_kernel(MlpTcArgs p) {
         const int b = c & 1;
         mbar_wait(B(T2Bars::d1_full + b), d1f_cnt[b] & 1); ++d1f_cnt[b];
         tc_fence_after();
+        if (tr_thread) TR(tl, 8 + c);
 #pragma unroll 1
         for (int part32 = 0; part32 < 2; ++part32) {
           const int col0 = col_half * 64 + part32 * 32;
@@ -347,12 +371,14 @@ mlp_tc3_kernel(MlpTcArgs p) {
         mbar_arrive(B(T2Bars::d1_empty + b));     // D1[b] may be overwritten
         fence_proxy_async_all();                   // scratch writes (generic proxy) -> bulk-copy reads (async proxy)
         mbar_arrive(B(T2Bars::h1_done + c));
+        if (tr_thread) TR(tl, 12 + c);
       }
 
       // ---- epilogue 2: s = sum_j w3[j] * relu(D2[row][j] + b2[j]); each warp of a lane quarter takes
       // 256 of the 512 columns (j ascending inside a half), lower half + upper half
       mbar_wait(B(T2Bars::d2_full), d2f_ph); d2f_ph ^= 1;
       tc_fence_after();
+      if (tr_thread) TR(tl, 26);
       float acc = 0.f;
 #pragma unroll 1
       for (int part32 = 0; part32 < 8; ++part32) {
@@ -372,6 +398,7 @@ mlp_tc3_kernel(MlpTcArgs p) {
       asm volatile("bar.sync 1, %0;" ::"n"(T2_EPI_THREADS) : "memory");
       if (col_half == 0 && row < nt) p.out[(int64_t)q * p.out_stride + t0 + row] = acc + part[row];
       asm volatile("bar.sync 1, %0;" ::"n"(T2_EPI_THREADS) : "memory");   // part[] is reused by the next tile
+      if (tr_thread) TR(tl, 27);
     }
   }
 

@@ -52,9 +52,10 @@ class Index:
         n_ep = enter_points.numel() if ops._is_torch(enter_points) else np.asarray(enter_points).size
         vals = (C.c_void_p * 2)(v[0][0], v[1][0])
         rss = (C.c_void_p * 2)(r[0][0], r[1][0])
+        n_vals = (C.c_int64 * 2)(*[(x.numel() if ops._is_torch(x) else np.asarray(x).size) for x in nbr_values])
         h = C.c_void_p()
         check(_lib.lib().nann_index_create(n, d, e_ptr, _NP2CODE[emb_dt], i_ptr, p_ptr, _NP2CODE[np.dtype(ep_dt)], n_ep,
-                                           vals, _NP2CODE[np.dtype(nv_dt)], rss, int(device), C.byref(h)))
+                                           vals, n_vals, _NP2CODE[np.dtype(nv_dt)], rss, int(device), C.byref(h)))
         return cls(h)
 
     @classmethod

@@ -1,0 +1,34 @@
+"""Per-tile pipeline timeline of the tensor-core scorer (CTA 0), from clock64() stamps."""
+import ctypes as C, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import nann_b200 as nb
+from nann_b200 import _lib, index as nix, scorer_weights as sw
+
+emb = nix.synthetic_corpus(400000, 128, seed=0)
+emb_d = torch.from_numpy(emb).cuda()
+sc = nb.Scorer.mlp(*sw.mlp_weights()); sc.set_precision(nb.SCORER_TENSOR)
+rng = np.random.default_rng(0)
+n = 148 * 128 * 40                        # 40 tiles per CTA
+ids = torch.from_numpy(rng.integers(0, emb.shape[0], n).astype(np.int32)).cuda()
+u = nix.synthetic_queries(emb, 1, seed=1)[0]
+nb.score_ids(sc, u, emb_d, ids)           # warm
+buf = torch.zeros(64 * 48, dtype=torch.int64, device="cuda")
+L = _lib.lib(); L.nann_debug_tc_trace.argtypes = [C.c_void_p]
+L.nann_debug_tc_trace(C.c_void_p(buf.data_ptr()))
+nb.score_ids(sc, u, emb_d, ids)
+L.nann_debug_tc_trace(None)
+t = buf.cpu().numpy().reshape(64, 48)
+names = {0: "epi gather start", 1: "epi x_ready", 2: "mma d2_empty ok", 3: "mma x_ready ok", 4: "mma c0 issued", 5: "mma c1 issued",
+         6: "mma c2 issued", 7: "mma c3 issued", 8: "epi d1_full c0", 9: "epi d1_full c1", 10: "epi d1_full c2", 11: "epi d1_full c3",
+         12: "epi c0 done", 13: "epi c1 done", 14: "epi c2 done", 15: "epi c3 done", 16: "mma phase2 start", 25: "mma d2 committed",
+         26: "epi d2_full ok", 27: "epi tile done", 28: "prod h1_done c0", 29: "prod h1_done c1", 30: "prod h1_done c2", 31: "prod h1_done c3",
+         32: "prod tile start", 33: "prod tile issued"}
+for s in range(8):
+    names[17 + s] = f"mma a_full s{s}"; names[34 + s] = f"prod A s{s} issue"
+for tile in (10, 11):
+    base = t[tile][0]
+    print(f"--- tile {tile} (cycles from its gather start; previous tile done at {t[tile-1][27]-base})")
+    for ev in sorted(names, key=lambda e: t[tile][e]):
+        if t[tile][ev]: print(f"{t[tile][ev]-base:9d}  {names[ev]}")
+print("tile period (cycles):", [int(t[i+1][0]-t[i][0]) for i in range(5, 15)])
