@@ -29,6 +29,7 @@ constexpr int TC_SCRATCH_BYTES = 8 * 2 * TC_SLAB_BYTES;  // h1: 8 K-slabs x (hi,
 struct MlpTcState {
   __half* W1img = nullptr;   // [4 chunks][2 planes][2 slabs][128 rows][64]   swizzled, 256 KB
   __half* W2img = nullptr;   // [8 slabs][2 halves][2 planes][256 rows][64]   swizzled, 1 MB
+  __half* W1img5 = nullptr;  // [8 chunks][2 planes][2 slabs][64 rows][64]    swizzled, 256 KB (mlp_tc5_kernel)
   int n_ctas = 0;
 };
 
@@ -165,7 +166,7 @@ struct MlpTcArgs {
   const float* table; const int32_t* ids; int64_t ids_stride; int64_t rows_stride;
   const int32_t* n_ptr; int n_fixed; int tiles_per_q; int B;
   const float* hu;        // [B][512]
-  const __half* W1img; const __half* W2img;
+  const __half* W1img; const __half* W2img; const __half* W1img5;
   const float* b2; const float* w3;
   uint8_t* scratch;       // [gridDim.x][TC_SCRATCH_BYTES]
   float* out; int64_t out_stride; const int32_t* status;
@@ -384,6 +385,7 @@ mlp_tc_kernel(MlpTcArgs p) {
 }  // namespace nann
 #include "scorer_mlp_tc2.cuh"
 #include "scorer_mlp_tc3.cuh"
+#include "scorer_mlp_tc5.cuh"
 namespace nann {
 
 // ---- weight images ---------------------------------------------------------------------------------
@@ -433,13 +435,17 @@ static nann_status mlp_tc_prepare(nann_scorer* s) {
   NANN_LAUNCH(transpose_kernel, (unsigned)ceil_div(128 * 512, 256), 256, 0, 0, s->W1xT, 128, 512, 512, 0, tmp.d);
   NANN_CUDA(cudaMemcpy2DAsync(W1.d + 128, 256 * 4, tmp.d, 128 * 4, 128 * 4, 512, cudaMemcpyDeviceToDevice, 0));
   NANN_LAUNCH(transpose_kernel, (unsigned)ceil_div(512 * 512, 256), 256, 0, 0, s->W2T, 512, 512, 512, 0, W2.d);
-  if (cudaMalloc(&st->W1img, 4 * TC_B_BYTES) != cudaSuccess || cudaMalloc(&st->W2img, 16 * TC_B_BYTES) != cudaSuccess) {
+  if (cudaMalloc(&st->W1img, 4 * TC_B_BYTES) != cudaSuccess || cudaMalloc(&st->W2img, 16 * TC_B_BYTES) != cudaSuccess ||
+      cudaMalloc(&st->W1img5, 8 * T5_STAGE) != cudaSuccess) {
     cudaGetLastError();
-    cudaFree(st->W1img); cudaFree(st->W2img); delete st;
+    cudaFree(st->W1img); cudaFree(st->W2img); cudaFree(st->W1img5); delete st;
     return fail(NANN_RESOURCE_EXHAUSTED, "OOM for tensor-core scorer state");
   }
   NANN_LAUNCH(tc_build_w1_kernel, (512 * 128) / 256, 256, 0, 0, W1.d, st->W1img);
   NANN_LAUNCH(tc_build_w2_kernel, (512 * 512) / 256, 256, 0, 0, W2.d, st->W2img);
+  NANN_LAUNCH(tc_build_w1_v5_kernel, (512 * 128) / 256, 256, 0, 0, W1.d, st->W1img5);
+  NANN_CUDA(cudaFuncSetAttribute(mlp_tc5_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, T5_SMEM_BYTES));
+  NANN_CUDA(cudaFuncSetAttribute(mlp_tc5_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, T5_SMEM_BYTES));
   NANN_CUDA(cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
   NANN_CUDA(cudaFuncSetAttribute(mlp_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
   NANN_CUDA(cudaFuncSetAttribute(mlp_tc3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
@@ -458,31 +464,34 @@ static nann_status mlp_tc_score(nann_scorer* s, const ScoreCall& c, cudaStream_t
   MlpTcArgs a{};
   a.table = c.table; a.ids = c.ids; a.ids_stride = c.ids_stride; a.rows_stride = c.rows_stride;
   a.n_ptr = c.n_ptr; a.n_fixed = c.n_fixed; a.tiles_per_q = (int)ceil_div(c.max_n, TC_M); a.B = c.B;
-  a.hu = c.hu; a.W1img = st->W1img; a.W2img = st->W2img; a.b2 = s->b2; a.w3 = s->w3;
+  a.hu = c.hu; a.W1img = st->W1img; a.W2img = st->W2img; a.W1img5 = st->W1img5; a.b2 = s->b2; a.w3 = s->w3;
   a.out = c.out; a.out_stride = c.out_stride; a.status = c.status;
   const int64_t n_tiles = (int64_t)a.B * a.tiles_per_q;
   NANN_TRY(tc_ws_ensure(c.ws, st->n_ctas, c.B, n_tiles));
   a.scratch = c.ws->scratch; a.tiles = c.ws->tiles; a.tile_total = c.ws->tile_start + c.B;
   a.trace = g_tc_trace;
-  // NANN_TC_KERNEL: 1 = bulk-synchronous cp.async kernel, 2 = warp-specialised TMA ring,
-  // 3 = 2 + dense tile list, 4 (default) = 3 launched as 2-CTA clusters with multicast weight stages
-  static const int version = [] { const char* e = std::getenv("NANN_TC_KERNEL"); return e ? atoi(e) : 4; }();
+  // NANN_TC_KERNEL: 1 = bulk-synchronous cp.async kernel, 2 = warp-specialised TMA ring (h1 via L2 scratch),
+  // 3 = 2 + dense tile list, 4 = 3 as 2-CTA clusters with multicast weight stages,
+  // 5 = on-chip h1 hand-off, two layer-2 passes (scorer_mlp_tc5.cuh), 6 = 5 as 2-CTA clusters (multicast)
+  static const int version = [] { const char* e = std::getenv("NANN_TC_KERNEL"); return e ? atoi(e) : 3; }();
   const int grid = (int)std::min<int64_t>(st->n_ctas, n_tiles);
   if (version == 1) { NANN_LAUNCH(mlp_tc_kernel, grid, TC_THREADS, TC_SMEM_BYTES, stm, a); return NANN_OK; }
   if (version == 2) { NANN_LAUNCH(mlp_tc2_kernel, grid, T2_THREADS, T2_SMEM_BYTES, stm, a); return NANN_OK; }
   NANN_LAUNCH(tile_scan_kernel, 1, 1024, 0, stm, c.n_ptr, c.n_fixed, c.status, c.B, c.ws->tile_start);
   NANN_LAUNCH(tile_fill_kernel, c.B, 128, 0, stm, c.ws->tile_start, c.B, c.ws->tiles);
   if (version == 3) { NANN_LAUNCH(mlp_tc3_kernel<1>, grid, T2_THREADS, T2_SMEM_BYTES, stm, a); return NANN_OK; }
+  if (version == 5) { NANN_LAUNCH(mlp_tc5_kernel<1>, grid, T5_THREADS, T5_SMEM_BYTES, stm, a); return NANN_OK; }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(st->n_ctas / 2 * 2));   // whole clusters; CTAs without tiles fall through
-  cfg.blockDim = dim3(T2_THREADS);
-  cfg.dynamicSmemBytes = T2_SMEM_BYTES;
+  cfg.blockDim = dim3(version == 6 ? T5_THREADS : T2_THREADS);
+  cfg.dynamicSmemBytes = version == 6 ? T5_SMEM_BYTES : T2_SMEM_BYTES;
   cfg.stream = stm;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  NANN_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc3_kernel<2>, a));
+  if (version == 6) NANN_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc5_kernel<2>, a));
+  else              NANN_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc3_kernel<2>, a));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return NANN_OK;
 }
@@ -497,7 +506,7 @@ namespace nann {
 static void mlp_tc_release(nann_scorer* s) {
   auto* st = (MlpTcState*)s->tc;
   if (!st) return;
-  cudaFree(st->W1img); cudaFree(st->W2img);
+  cudaFree(st->W1img); cudaFree(st->W2img); cudaFree(st->W1img5);
   delete st;
   s->tc = nullptr;
 }

@@ -26,9 +26,15 @@ names = {0: "epi gather start", 1: "epi x_ready", 2: "mma d2_empty ok", 3: "mma 
          32: "prod tile start", 33: "prod tile issued"}
 for s in range(8):
     names[17 + s] = f"mma a_full s{s}"; names[34 + s] = f"prod A s{s} issue"
+if os.environ.get("NANN_TC_KERNEL", "3") in ("5", "6"):
+    names = {0: "mma x_ready ok", 1: "mma pass0 issued", 2: "mma pass1 issued", 20: "B loop top", 21: "B epi2(0) done",
+             22: "B x_free ok", 23: "B gather done", 25: "B epi2(1) done"}
+    for h in range(2):
+        for c in range(8):
+            names[4 + h * 8 + c] = f"A slab h{h} c{c} written"; names[26 + h * 8 + c] = f"mma P2 h{h} c{c} issued"
 for tile in (10, 11):
     base = t[tile][0]
-    print(f"--- tile {tile} (cycles from its gather start; previous tile done at {t[tile-1][27]-base})")
+    print(f"--- tile {tile} (cycles from event 0)")
     for ev in sorted(names, key=lambda e: t[tile][e]):
         if t[tile][ev]: print(f"{t[tile][ev]-base:9d}  {names[ev]}")
 print("tile period (cycles):", [int(t[i+1][0]-t[i][0]) for i in range(5, 15)])
