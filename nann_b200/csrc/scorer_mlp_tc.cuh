@@ -156,6 +156,17 @@ __device__ __forceinline__ void split_f16(float a, __half& hi, __half& lo) {
   hi = __float2half_rn(a);
   lo = __float2half_rn(a - __half2float(hi));
 }
+// Two values at once with the PACKED converts (cvt.rn.f16x2.f32 -> F2FP.PACK_AB, ALU rate); the scalar
+// F2F.F16.F32 above runs on the 16-lane/SM conversion pipe and was THE bottleneck of every epilogue
+// (profiles/r01_tc_timeline_v5.log: 4.3k cycles per 64-neuron chunk for 1.4k cycles of MMA).
+// Same results bit for bit: both are round-to-nearest-even converts of the same fp32 values.
+__device__ __forceinline__ void split2_f16(float a0, float a1, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(a0, a1);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a0 - hf.x, a1 - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
 
 // contiguous global -> shared copy of `bytes` (multiple of 16*TC_THREADS) with cp.async
 __device__ __forceinline__ void tc_copy_async(uint8_t* dst, const uint8_t* __restrict__ src, int bytes, int tid) {
@@ -234,17 +245,12 @@ mlp_tc_kernel(MlpTcArgs p) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int c = warp * 16 + i0 + j;
-          __half h[4], l[4];
-          split_f16(v[j].x, h[0], l[0]); split_f16(v[j].y, h[1], l[1]);
-          split_f16(v[j].z, h[2], l[2]); split_f16(v[j].w, h[3], l[3]);
+          uint32_t h01, l01, h23, l23;
+            split2_f16(v[j].x, v[j].y, h01, l01); split2_f16(v[j].z, v[j].w, h23, l23);
           const int k = lane * 4, slab = k >> 6, chunk = (k & 63) >> 3, sub = (k & 7) * 2;
           const uint32_t off = slab * TC_SLAB_BYTES + sw128_chunk_off(c, chunk) + sub;
-          *reinterpret_cast<uint2*>(sA + off) = make_uint2(
-              (uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16),
-              (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16));
-          *reinterpret_cast<uint2*>(sA + 2 * TC_SLAB_BYTES + off) = make_uint2(
-              (uint32_t)__half_as_ushort(l[0]) | ((uint32_t)__half_as_ushort(l[1]) << 16),
-              (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16));
+          *reinterpret_cast<uint2*>(sA + off) = make_uint2(h01, h23);
+          *reinterpret_cast<uint2*>(sA + 2 * TC_SLAB_BYTES + off) = make_uint2(l01, l23);
         }
       }
     }
@@ -272,10 +278,7 @@ mlp_tc_kernel(MlpTcArgs p) {
             float a0 = __uint_as_float(v[ch * 8 + 2 * e]) + huq[neuron0 + ch * 8 + 2 * e];
             float a1 = __uint_as_float(v[ch * 8 + 2 * e + 1]) + huq[neuron0 + ch * 8 + 2 * e + 1];
             a0 = a0 > 0.f ? a0 : 0.f; a1 = a1 > 0.f ? a1 : 0.f;
-            __half h0, l0, h1, l1;
-            split_f16(a0, h0, l0); split_f16(a1, h1, l1);
-            hw[e] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-            lw[e] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+            split2_f16(a0, a1, hw[e], lw[e]);
           }
           const int chunk = ((neuron0 & 63) >> 3) + ch;
           const uint32_t off = (uint32_t)slab * 2 * TC_SLAB_BYTES + sw128_chunk_off(row, chunk);
