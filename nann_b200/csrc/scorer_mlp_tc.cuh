@@ -144,6 +144,8 @@ __host__ __device__ __forceinline__ uint32_t sw128_chunk_off(int r, int c) {
   return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
 }
 
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
 // 16-byte streaming load of a table row chunk; NOT volatile so several can be put in flight
 __device__ __forceinline__ float4 ld_row16(const float* p) {
   float4 v;
@@ -482,11 +484,11 @@ static nann_status mlp_tc_score(nann_scorer* s, const ScoreCall& c, cudaStream_t
   if (version == 2) { NANN_LAUNCH(mlp_tc2_kernel, grid, T2_THREADS, T2_SMEM_BYTES, stm, a); return NANN_OK; }
   NANN_LAUNCH(tile_scan_kernel, 1, 1024, 0, stm, c.n_ptr, c.n_fixed, c.status, c.B, c.ws->tile_start);
   NANN_LAUNCH(tile_fill_kernel, c.B, 128, 0, stm, c.ws->tile_start, c.B, c.ws->tiles);
-  if (version == 3) { NANN_LAUNCH(mlp_tc3_kernel<1>, grid, T2_THREADS, T2_SMEM_BYTES, stm, a); return NANN_OK; }
+  if (version == 3) { NANN_LAUNCH(mlp_tc3_kernel<1>, grid, T3_THREADS, T2_SMEM_BYTES, stm, a); return NANN_OK; }
   if (version == 5) { NANN_LAUNCH(mlp_tc5_kernel<1>, grid, T5_THREADS, T5_SMEM_BYTES, stm, a); return NANN_OK; }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(st->n_ctas / 2 * 2));   // whole clusters; CTAs without tiles fall through
-  cfg.blockDim = dim3(version == 6 ? T5_THREADS : T2_THREADS);
+  cfg.blockDim = dim3(version == 6 ? T5_THREADS : T3_THREADS);
   cfg.dynamicSmemBytes = version == 6 ? T5_SMEM_BYTES : T2_SMEM_BYTES;
   cfg.stream = stm;
   cudaLaunchAttribute attr[1];

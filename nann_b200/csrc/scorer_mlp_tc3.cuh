@@ -59,8 +59,15 @@ __global__ void tile_fill_kernel(const int32_t* __restrict__ tile_start, int B, 
   for (int t = threadIdx.x; t < e - s; t += blockDim.x) tiles[s + t] = make_int2(q, t);
 }
 
+constexpr int T3_THREADS = T2_THREADS + 32;   // + one loader warp (h1 slabs: L2 scratch -> shared, cp.async)
+
+__device__ __forceinline__ void st_global_v8(void* p, uint4 a, uint4 b) {   // one 32-byte store (STG.256)
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+}
+
 template <int CL>
-__global__ void __launch_bounds__(T2_THREADS, 1)
+__global__ void __launch_bounds__(T3_THREADS, 1)
 mlp_tc3_kernel(MlpTcArgs p) {
   // cluster rank / peers (CL == 1: a plain launch, rank 0)
   uint32_t cta_rank = 0;
@@ -128,8 +135,6 @@ mlp_tc3_kernel(MlpTcArgs p) {
     // =============================== producer ===============================
     if (lane == 0) {
       uint32_t it = 0;                         // ring stage counter across tiles
-      uint32_t a_cnt[2] = {0, 0};              // uses of the A buffers
-      uint32_t h1_ph = 0;                      // parity of h1_done[*] (one completion per tile each)
       auto ring_load = [&](const void* src) {
         const uint32_t slot = it % T2_NS, ph = (it / T2_NS) & 1;
         mbar_wait(B(T2Bars::empty + slot), ph ^ 1);          // released by the MMA threads of ALL CTAs of the cluster
@@ -154,13 +159,6 @@ mlp_tc3_kernel(MlpTcArgs p) {
           ring_load((const uint8_t*)p.W1img + (size_t)c * TC_B_BYTES + T2_STAGE);
         }
         for (int s = 0; s < 8; ++s) {
-          if ((s & 1) == 0) { mbar_wait(B(T2Bars::h1_done + (s >> 1)), h1_ph); TR(tl, 28 + (s >> 1)); }   // epilogue of chunk s/2 wrote slabs s, s+1
-          const int b = s & 1;
-          mbar_wait(B(T2Bars::a_empty + b), a_cnt[b] & 1);                        // x tile / slab s-2 no longer read
-          TR(tl, 34 + s);
-          mbar_expect_tx(B(T2Bars::a_full + b), T2_STAGE);
-          bulk_g2s(sX_u + b * T2_STAGE, scratch + (size_t)s * T2_STAGE, T2_STAGE, B(T2Bars::a_full + b));
-          ++a_cnt[b];
           for (int h = 0; h < 2; ++h) {
             const uint8_t* w = (const uint8_t*)p.W2img + (size_t)(s * 2 + h) * TC_B_BYTES;
             ring_load(w);
@@ -168,7 +166,6 @@ mlp_tc3_kernel(MlpTcArgs p) {
           }
         }
         TR(tl, 33);
-        h1_ph ^= 1;
       }
     }
   } else if (warp == 1) {
@@ -269,6 +266,32 @@ mlp_tc3_kernel(MlpTcArgs p) {
         TR(tl, 25);
       }
     }
+  } else if (warp == 2 + T2_EPI_WARPS) {
+    // =============================== loader: h1 slabs, L2 scratch -> shared ===============================
+    // cp.async (generic proxy, like the epilogue's st.global that produced the data): no cross-proxy
+    // fence on global memory is needed, only the cheap shared-memory one before the MMAs read the slab.
+    uint32_t a_cnt[2] = {0, 0}, h1_ph = 0;
+    int tl = -1;
+    for (int64_t g = g_first; g < n_tiles; g += g_step) {
+      int q, t0, nt;
+      if (!tile_info(g, q, t0, nt)) continue;
+      ++tl;
+      for (int s = 0; s < 8; ++s) {
+        if ((s & 1) == 0) { mbar_wait(B(T2Bars::h1_done + (s >> 1)), h1_ph); if (lane == 0) TR(tl, 28 + (s >> 1)); }
+        const int b = s & 1;
+        mbar_wait(B(T2Bars::a_empty + b), a_cnt[b] & 1); ++a_cnt[b];        // x tile / slab s-2 no longer read
+        if (lane == 0) TR(tl, 34 + s);
+        uint8_t* dst = sX + b * T2_STAGE;
+        const uint8_t* src = scratch + (size_t)s * T2_STAGE;
+#pragma unroll 8
+        for (int o = lane * 16; o < T2_STAGE; o += 32 * 16) cp_async16(dst + o, src + o);
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(B(T2Bars::a_full + b));
+      }
+      h1_ph ^= 1;
+    }
   } else {
     // =============================== gather + epilogues (warps 2..9) ===============================
     const int ew = warp - 2;                  // 0..7
@@ -344,24 +367,36 @@ mlp_tc3_kernel(MlpTcArgs p) {
           const int neuron0 = c * 128 + col0;
           const int slab = neuron0 >> 6;
 #pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
-            uint32_t hw[4], lw[4];
+          for (int cp = 0; cp < 2; ++cp) {                      // two 16-column pairs of 8-column chunks
+            uint4 hq[2], lq[2];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float a0 = __uint_as_float(v[ch * 8 + 2 * e]) + __ldg(huq + neuron0 + ch * 8 + 2 * e);
-              float a1 = __uint_as_float(v[ch * 8 + 2 * e + 1]) + __ldg(huq + neuron0 + ch * 8 + 2 * e + 1);
-              a0 = a0 > 0.f ? a0 : 0.f; a1 = a1 > 0.f ? a1 : 0.f;
-              split2_f16(a0, a1, hw[e], lw[e]);
+            for (int hf = 0; hf < 2; ++hf) {
+              const int ch = cp * 2 + hf;
+              const float4 ha = ldg4(huq + neuron0 + ch * 8), hb = ldg4(huq + neuron0 + ch * 8 + 4);
+              const float hv[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+              uint32_t hw[4], lw[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float a0 = __uint_as_float(v[ch * 8 + 2 * e]) + hv[2 * e];
+                float a1 = __uint_as_float(v[ch * 8 + 2 * e + 1]) + hv[2 * e + 1];
+                a0 = a0 > 0.f ? a0 : 0.f; a1 = a1 > 0.f ? a1 : 0.f;
+                split2_f16(a0, a1, hw[e], lw[e]);
+              }
+              hq[hf] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+              lq[hf] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
             }
-            const int chunk = ((neuron0 & 63) >> 3) + ch;
-            const uint32_t off = (uint32_t)slab * 2 * TC_SLAB_BYTES + sw128_chunk_off(row, chunk);
-            *reinterpret_cast<uint4*>(scratch + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-            *reinterpret_cast<uint4*>(scratch + off + TC_SLAB_BYTES) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            // chunks c, c+1 (c even) land in one 32-byte block of the swizzled row; odd rows swap them
+            const int c = ((neuron0 & 63) >> 3) + cp * 2;
+            const int sw = (c ^ (row & 7));
+            const uint32_t off = (uint32_t)slab * 2 * TC_SLAB_BYTES + (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((sw & ~1) << 4));
+            const bool swap = (row & 1) != 0;
+            st_global_v8(scratch + off, swap ? hq[1] : hq[0], swap ? hq[0] : hq[1]);
+            st_global_v8(scratch + off + TC_SLAB_BYTES, swap ? lq[1] : lq[0], swap ? lq[0] : lq[1]);
           }
         }
         tc_fence_before();
         mbar_arrive(B(T2Bars::d1_empty + b));     // D1[b] may be overwritten
-        fence_proxy_async_all();                   // scratch writes (generic proxy) -> bulk-copy reads (async proxy)
+        __threadfence_block();                     // scratch stores before the arrive; the loader reads them with cp.async
         mbar_arrive(B(T2Bars::h1_done + c));
         if (tr_thread) TR(tl, 12 + c);
       }
@@ -378,10 +413,13 @@ mlp_tc3_kernel(MlpTcArgs p) {
         uint32_t v[32];
         tc_ld32(tmem + ((uint32_t)(lane_q * 32) << 16) + (uint32_t)col0, v);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float a = __uint_as_float(v[j]) + __ldg(p.b2 + col0 + j);
-          a = a > 0.f ? a : 0.f;
-          acc = fmaf(__ldg(p.w3 + col0 + j), a, acc);
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 bb = ldg4(p.b2 + col0 + j4 * 4), ww = ldg4(p.w3 + col0 + j4 * 4);
+          float a;
+          a = __uint_as_float(v[j4 * 4 + 0]) + bb.x; a = a > 0.f ? a : 0.f; acc = fmaf(ww.x, a, acc);
+          a = __uint_as_float(v[j4 * 4 + 1]) + bb.y; a = a > 0.f ? a : 0.f; acc = fmaf(ww.y, a, acc);
+          a = __uint_as_float(v[j4 * 4 + 2]) + bb.z; a = a > 0.f ? a : 0.f; acc = fmaf(ww.z, a, acc);
+          a = __uint_as_float(v[j4 * 4 + 3]) + bb.w; a = a > 0.f ? a : 0.f; acc = fmaf(ww.w, a, acc);
         }
       }
       tc_fence_before();

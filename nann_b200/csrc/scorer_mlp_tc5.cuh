@@ -40,7 +40,6 @@ struct T5Bars {
   static constexpr int count = 22;
 };
 
-__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
 template <int CL>
 __global__ void __launch_bounds__(T5_THREADS, 1)
