@@ -359,11 +359,15 @@ mlp_tc3_kernel(MlpTcArgs p) {
         mbar_wait(B(T2Bars::d1_full + b), d1f_cnt[b] & 1); ++d1f_cnt[b];
         tc_fence_after();
         if (tr_thread) TR(tl, 8 + c);
-#pragma unroll 1
+        uint32_t va[32], vb[32];
+        tc_ld32_nowait(tmem + ((uint32_t)(lane_q * 32) << 16) + (uint32_t)(b * 128 + col_half * 64), va);
+        tc_ld32_nowait(tmem + ((uint32_t)(lane_q * 32) << 16) + (uint32_t)(b * 128 + col_half * 64 + 32), vb);
+        tc_ld_wait_dep(va);
+        tc_ld_wait_dep(vb);
+#pragma unroll
         for (int part32 = 0; part32 < 2; ++part32) {
           const int col0 = col_half * 64 + part32 * 32;
-          uint32_t v[32];
-          tc_ld32(tmem + ((uint32_t)(lane_q * 32) << 16) + (uint32_t)(b * 128 + col0), v);
+          const uint32_t (&v)[32] = part32 ? vb : va;
           const int neuron0 = c * 128 + col0;
           const int slab = neuron0 >> 6;
 #pragma unroll
@@ -407,19 +411,30 @@ mlp_tc3_kernel(MlpTcArgs p) {
       tc_fence_after();
       if (tr_thread) TR(tl, 26);
       float acc = 0.f;
-#pragma unroll 1
-      for (int part32 = 0; part32 < 8; ++part32) {
-        const int col0 = col_half * 256 + part32 * 32;
-        uint32_t v[32];
-        tc_ld32(tmem + ((uint32_t)(lane_q * 32) << 16) + (uint32_t)col0, v);
+      {
+        const uint32_t tbase = tmem + ((uint32_t)(lane_q * 32) << 16) + (uint32_t)(col_half * 256);
+        uint32_t v0[32], v1[32];
+        auto consume = [&](const uint32_t (&v)[32], int col0) {
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 bb = ldg4(p.b2 + col0 + j4 * 4), ww = ldg4(p.w3 + col0 + j4 * 4);
-          float a;
-          a = __uint_as_float(v[j4 * 4 + 0]) + bb.x; a = a > 0.f ? a : 0.f; acc = fmaf(ww.x, a, acc);
-          a = __uint_as_float(v[j4 * 4 + 1]) + bb.y; a = a > 0.f ? a : 0.f; acc = fmaf(ww.y, a, acc);
-          a = __uint_as_float(v[j4 * 4 + 2]) + bb.z; a = a > 0.f ? a : 0.f; acc = fmaf(ww.z, a, acc);
-          a = __uint_as_float(v[j4 * 4 + 3]) + bb.w; a = a > 0.f ? a : 0.f; acc = fmaf(ww.w, a, acc);
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 bb = ldg4(p.b2 + col0 + j4 * 4), ww = ldg4(p.w3 + col0 + j4 * 4);
+            float a;
+            a = __uint_as_float(v[j4 * 4 + 0]) + bb.x; a = a > 0.f ? a : 0.f; acc = fmaf(ww.x, a, acc);
+            a = __uint_as_float(v[j4 * 4 + 1]) + bb.y; a = a > 0.f ? a : 0.f; acc = fmaf(ww.y, a, acc);
+            a = __uint_as_float(v[j4 * 4 + 2]) + bb.z; a = a > 0.f ? a : 0.f; acc = fmaf(ww.z, a, acc);
+            a = __uint_as_float(v[j4 * 4 + 3]) + bb.w; a = a > 0.f ? a : 0.f; acc = fmaf(ww.w, a, acc);
+          }
+        };
+        tc_ld32_nowait(tbase, v0);
+        tc_ld_wait_dep(v0);
+#pragma unroll
+        for (int pp = 0; pp < 4; ++pp) {        // 8 blocks of 32 columns, the next one in flight while one is consumed
+          tc_ld32_nowait(tbase + (uint32_t)((2 * pp + 1) * 32), v1);
+          consume(v0, col_half * 256 + (2 * pp) * 32);
+          tc_ld_wait_dep(v1);
+          if (pp < 3) tc_ld32_nowait(tbase + (uint32_t)((2 * pp + 2) * 32), v0);
+          consume(v1, col_half * 256 + (2 * pp + 1) * 32);
+          if (pp < 3) tc_ld_wait_dep(v0);
         }
       }
       tc_fence_before();
