@@ -182,6 +182,32 @@ __device__ __forceinline__ void split_f16(float a, __half& hi, __half& lo) {
   hi = __float2half_rn(a);
   lo = __float2half_rn(a - __half2float(hi));
 }
+// Blackwell packed fp32 pairs (FADD2 / FFMA2): two IEEE fp32 operations per issued instruction
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  float2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(*reinterpret_cast<unsigned long long*>(&d))
+      : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)));
+  return d;
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(*reinterpret_cast<unsigned long long*>(&d))
+      : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)),
+        "l"(*reinterpret_cast<const unsigned long long*>(&c)));
+  return d;
+}
+// relu(x + bias) for a pair, then the (hi, lo) fp16 split of both values
+__device__ __forceinline__ void bias_relu_split2(uint32_t r0, uint32_t r1, float2 bias, uint32_t& hi, uint32_t& lo) {
+  float2 a = add2(make_float2(__uint_as_float(r0), __uint_as_float(r1)), bias);
+  a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f);
+  const __half2 h = __floats2half2_rn(a.x, a.y);
+  const float2 hf = __half22float2(h);
+  const float2 d = fma2(hf, make_float2(-1.f, -1.f), a);      // a - hf, exact
+  const __half2 l = __floats2half2_rn(d.x, d.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
 // Two values at once with the PACKED converts (cvt.rn.f16x2.f32 -> F2FP.PACK_AB, ALU rate); the scalar
 // F2F.F16.F32 above runs on the 16-lane/SM conversion pipe and was THE bottleneck of every epilogue
 // (profiles/r01_tc_timeline_v5.log: 4.3k cycles per 64-neuron chunk for 1.4k cycles of MMA).

@@ -283,8 +283,15 @@ mlp_tc3_kernel(MlpTcArgs p) {
         if (lane == 0) TR(tl, 34 + s);
         uint8_t* dst = sX + b * T2_STAGE;
         const uint8_t* src = scratch + (size_t)s * T2_STAGE;
-#pragma unroll 8
-        for (int o = lane * 16; o < T2_STAGE; o += 32 * 16) cp_async16(dst + o, src + o);
+        // chunk-major scratch -> K-major SWIZZLE_128B tile: consecutive lanes read consecutive 16-B chunks of
+        // the scratch (coalesced) and scatter them to their swizzled place in shared memory
+#pragma unroll 4
+        for (int idx = lane; idx < 8 * TC_M; idx += 32) {
+          const int chunk = idx >> 7, r = idx & (TC_M - 1);
+          const uint32_t o = sw128_chunk_off(r, chunk);
+          cp_async16(dst + o, src + (size_t)idx * 16);                                   // hi plane
+          cp_async16(dst + TC_SLAB_BYTES + o, src + TC_SLAB_BYTES + (size_t)idx * 16);  // lo plane
+        }
         asm volatile("cp.async.wait_all;" ::: "memory");
         fence_proxy_async();
         __syncwarp();
@@ -364,6 +371,7 @@ mlp_tc3_kernel(MlpTcArgs p) {
         tc_ld32_nowait(tmem + ((uint32_t)(lane_q * 32) << 16) + (uint32_t)(b * 128 + col_half * 64 + 32), vb);
         tc_ld_wait_dep(va);
         tc_ld_wait_dep(vb);
+        if (tr_thread && c == 1) TR(tl, 42);
 #pragma unroll
         for (int part32 = 0; part32 < 2; ++part32) {
           const int col0 = col_half * 64 + part32 * 32;
@@ -371,36 +379,26 @@ mlp_tc3_kernel(MlpTcArgs p) {
           const int neuron0 = c * 128 + col0;
           const int slab = neuron0 >> 6;
 #pragma unroll
-          for (int cp = 0; cp < 2; ++cp) {                      // two 16-column pairs of 8-column chunks
-            uint4 hq[2], lq[2];
-#pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
-              const int ch = cp * 2 + hf;
-              const float4 ha = ldg4(huq + neuron0 + ch * 8), hb = ldg4(huq + neuron0 + ch * 8 + 4);
-              const float hv[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
-              uint32_t hw[4], lw[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float a0 = __uint_as_float(v[ch * 8 + 2 * e]) + hv[2 * e];
-                float a1 = __uint_as_float(v[ch * 8 + 2 * e + 1]) + hv[2 * e + 1];
-                a0 = a0 > 0.f ? a0 : 0.f; a1 = a1 > 0.f ? a1 : 0.f;
-                split2_f16(a0, a1, hw[e], lw[e]);
-              }
-              hq[hf] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-              lq[hf] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-            }
-            // chunks c, c+1 (c even) land in one 32-byte block of the swizzled row; odd rows swap them
-            const int c = ((neuron0 & 63) >> 3) + cp * 2;
-            const int sw = (c ^ (row & 7));
-            const uint32_t off = (uint32_t)slab * 2 * TC_SLAB_BYTES + (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((sw & ~1) << 4));
-            const bool swap = (row & 1) != 0;
-            st_global_v8(scratch + off, swap ? hq[1] : hq[0], swap ? hq[0] : hq[1]);
-            st_global_v8(scratch + off + TC_SLAB_BYTES, swap ? lq[1] : lq[0], swap ? lq[0] : lq[1]);
+          for (int ch = 0; ch < 4; ++ch) {                      // 8 columns -> one 16-byte chunk per plane
+            const float4 ha = ldg4(huq + neuron0 + ch * 8), hb = ldg4(huq + neuron0 + ch * 8 + 4);
+            uint32_t hw[4], lw[4];
+            bias_relu_split2(v[ch * 8 + 0], v[ch * 8 + 1], make_float2(ha.x, ha.y), hw[0], lw[0]);
+            bias_relu_split2(v[ch * 8 + 2], v[ch * 8 + 3], make_float2(ha.z, ha.w), hw[1], lw[1]);
+            bias_relu_split2(v[ch * 8 + 4], v[ch * 8 + 5], make_float2(hb.x, hb.y), hw[2], lw[2]);
+            bias_relu_split2(v[ch * 8 + 6], v[ch * 8 + 7], make_float2(hb.z, hb.w), hw[3], lw[3]);
+            // scratch slab layout is CHUNK-major: [plane][chunk 0..7][row 0..127][16 B]: a warp (32 rows, one
+            // chunk) stores 512 contiguous bytes; the loader applies the UMMA swizzle when it copies to smem
+            const int chunk = ((neuron0 & 63) >> 3) + ch;
+            uint8_t* dstp = scratch + (size_t)slab * 2 * TC_SLAB_BYTES + ((size_t)chunk * TC_M + row) * 16;
+            *reinterpret_cast<uint4*>(dstp) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            *reinterpret_cast<uint4*>(dstp + TC_SLAB_BYTES) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
           }
         }
+        if (tr_thread && c == 1) TR(tl, 43);
         tc_fence_before();
         mbar_arrive(B(T2Bars::d1_empty + b));     // D1[b] may be overwritten
-        __threadfence_block();                     // scratch stores before the arrive; the loader reads them with cp.async
+        __threadfence_block();
+        if (tr_thread && c == 1) TR(tl, 44);                     // scratch stores before the arrive; the loader reads them with cp.async
         mbar_arrive(B(T2Bars::h1_done + c));
         if (tr_thread) TR(tl, 12 + c);
       }
@@ -414,15 +412,16 @@ mlp_tc3_kernel(MlpTcArgs p) {
       {
         const uint32_t tbase = tmem + ((uint32_t)(lane_q * 32) << 16) + (uint32_t)(col_half * 256);
         uint32_t v0[32], v1[32];
+        float2 acc2 = make_float2(0.f, 0.f);
         auto consume = [&](const uint32_t (&v)[32], int col0) {
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
             const float4 bb = ldg4(p.b2 + col0 + j4 * 4), ww = ldg4(p.w3 + col0 + j4 * 4);
-            float a;
-            a = __uint_as_float(v[j4 * 4 + 0]) + bb.x; a = a > 0.f ? a : 0.f; acc = fmaf(ww.x, a, acc);
-            a = __uint_as_float(v[j4 * 4 + 1]) + bb.y; a = a > 0.f ? a : 0.f; acc = fmaf(ww.y, a, acc);
-            a = __uint_as_float(v[j4 * 4 + 2]) + bb.z; a = a > 0.f ? a : 0.f; acc = fmaf(ww.z, a, acc);
-            a = __uint_as_float(v[j4 * 4 + 3]) + bb.w; a = a > 0.f ? a : 0.f; acc = fmaf(ww.w, a, acc);
+            float2 z0 = add2(make_float2(__uint_as_float(v[j4 * 4 + 0]), __uint_as_float(v[j4 * 4 + 1])), make_float2(bb.x, bb.y));
+            float2 z1 = add2(make_float2(__uint_as_float(v[j4 * 4 + 2]), __uint_as_float(v[j4 * 4 + 3])), make_float2(bb.z, bb.w));
+            z0.x = fmaxf(z0.x, 0.f); z0.y = fmaxf(z0.y, 0.f); z1.x = fmaxf(z1.x, 0.f); z1.y = fmaxf(z1.y, 0.f);
+            acc2 = fma2(make_float2(ww.x, ww.y), z0, acc2);
+            acc2 = fma2(make_float2(ww.z, ww.w), z1, acc2);
           }
         };
         tc_ld32_nowait(tbase, v0);
@@ -436,7 +435,9 @@ mlp_tc3_kernel(MlpTcArgs p) {
           consume(v1, col_half * 256 + (2 * pp + 1) * 32);
           if (pp < 3) tc_ld_wait_dep(v0);
         }
+        acc = acc2.x + acc2.y;
       }
+      if (tr_thread) TR(tl, 45);
       tc_fence_before();
       mbar_arrive(B(T2Bars::d2_empty));           // TMEM is free for the next tile's phase 1
       if (col_half == 1) part[row] = acc;

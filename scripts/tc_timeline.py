@@ -24,6 +24,7 @@ names = {0: "epi gather start", 1: "epi x_ready", 2: "mma d2_empty ok", 3: "mma 
          12: "epi c0 done", 13: "epi c1 done", 14: "epi c2 done", 15: "epi c3 done", 16: "mma phase2 start", 25: "mma d2 committed",
          26: "epi d2_full ok", 27: "epi tile done", 28: "prod h1_done c0", 29: "prod h1_done c1", 30: "prod h1_done c2", 31: "prod h1_done c3",
          32: "prod tile start", 33: "prod tile issued"}
+names.update({42: "epi c1 tmem loaded", 43: "epi c1 stores issued", 44: "epi c1 fence done", 45: "epi2 math done"})
 for s in range(8):
     names[17 + s] = f"mma a_full s{s}"; names[34 + s] = f"prod A s{s} issue"
 if os.environ.get("NANN_TC_KERNEL", "3") in ("5", "6"):
