@@ -27,6 +27,7 @@ constexpr int TC_SLAB_BYTES = TC_M * 128;      // [128 rows][64 fp16] = 16 KB
 constexpr int TC_SCRATCH_BYTES = 8 * 2 * TC_SLAB_BYTES;  // h1: 8 K-slabs x (hi,lo) = 256 KB per CTA
 
 struct MlpTcState {
+  float h_b2[MLP_H], h_w3[MLP_H];   // host copies for the by-value kernel parameters
   __half* W1img = nullptr;   // [4 chunks][2 planes][2 slabs][128 rows][64]   swizzled, 256 KB
   __half* W2img = nullptr;   // [8 slabs][2 halves][2 planes][256 rows][64]   swizzled, 1 MB
   __half* W1img5 = nullptr;  // [8 chunks][2 planes][2 slabs][64 rows][64]    swizzled, 256 KB (mlp_tc5_kernel)
@@ -235,6 +236,11 @@ struct MlpTcArgs {
   float* out; int64_t out_stride; const int32_t* status;
   const int2* tiles; const int32_t* tile_total;   // dense tile list (mlp_tc3_kernel)
   long long* trace;                               // optional CTA-0 timeline [64 tiles][48 events] (debug)
+  // b2 / w3 by value: kernel parameters live in the constant bank, so the layer-2 epilogue reads them with
+  // uniform constant loads.  (With ~225 KB of shared memory per CTA the L1 data cache is a few KB: __ldg of
+  // these vectors missed to L2 on almost every access and throttled the epilogues.)
+  float b2c[MLP_H];
+  float w3c[MLP_H];
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -503,8 +509,10 @@ static nann_status mlp_tc_prepare(nann_scorer* s) {
   NANN_CUDA(cudaFuncSetAttribute(mlp_tc5_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, T5_SMEM_BYTES));
   NANN_CUDA(cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
   NANN_CUDA(cudaFuncSetAttribute(mlp_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
-  NANN_CUDA(cudaFuncSetAttribute(mlp_tc3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
-  NANN_CUDA(cudaFuncSetAttribute(mlp_tc3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
+  NANN_CUDA(cudaFuncSetAttribute(mlp_tc3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, T3_SMEM_BYTES));
+  NANN_CUDA(cudaFuncSetAttribute(mlp_tc3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, T3_SMEM_BYTES));
+  NANN_CUDA(cudaMemcpy(st->h_b2, s->b2, sizeof(st->h_b2), cudaMemcpyDeviceToHost));
+  NANN_CUDA(cudaMemcpy(st->h_w3, s->w3, sizeof(st->h_w3), cudaMemcpyDeviceToHost));
   NANN_CUDA(cudaDeviceSynchronize());
   s->tc = st;
   return NANN_OK;
@@ -521,6 +529,8 @@ static nann_status mlp_tc_score(nann_scorer* s, const ScoreCall& c, cudaStream_t
   a.n_ptr = c.n_ptr; a.n_fixed = c.n_fixed; a.tiles_per_q = (int)ceil_div(c.max_n, TC_M); a.B = c.B;
   a.hu = c.hu; a.W1img = st->W1img; a.W2img = st->W2img; a.W1img5 = st->W1img5; a.b2 = s->b2; a.w3 = s->w3;
   a.out = c.out; a.out_stride = c.out_stride; a.status = c.status;
+  memcpy(a.b2c, st->h_b2, sizeof(a.b2c));
+  memcpy(a.w3c, st->h_w3, sizeof(a.w3c));
   const int64_t n_tiles = (int64_t)a.B * a.tiles_per_q;
   NANN_TRY(tc_ws_ensure(c.ws, st->n_ctas, c.B, n_tiles));
   a.scratch = c.ws->scratch; a.tiles = c.ws->tiles; a.tile_total = c.ws->tile_start + c.B;
@@ -534,12 +544,12 @@ static nann_status mlp_tc_score(nann_scorer* s, const ScoreCall& c, cudaStream_t
   if (version == 2) { NANN_LAUNCH(mlp_tc2_kernel, grid, T2_THREADS, T2_SMEM_BYTES, stm, a); return NANN_OK; }
   NANN_LAUNCH(tile_scan_kernel, 1, 1024, 0, stm, c.n_ptr, c.n_fixed, c.status, c.B, c.ws->tile_start);
   NANN_LAUNCH(tile_fill_kernel, c.B, 128, 0, stm, c.ws->tile_start, c.B, c.ws->tiles);
-  if (version == 3) { NANN_LAUNCH(mlp_tc3_kernel<1>, grid, T3_THREADS, T2_SMEM_BYTES, stm, a); return NANN_OK; }
+  if (version == 3) { NANN_LAUNCH(mlp_tc3_kernel<1>, grid, T3_THREADS, T3_SMEM_BYTES, stm, a); return NANN_OK; }
   if (version == 5) { NANN_LAUNCH(mlp_tc5_kernel<1>, grid, T5_THREADS, T5_SMEM_BYTES, stm, a); return NANN_OK; }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(st->n_ctas / 2 * 2));   // whole clusters; CTAs without tiles fall through
   cfg.blockDim = dim3(version == 6 ? T5_THREADS : T3_THREADS);
-  cfg.dynamicSmemBytes = version == 6 ? T5_SMEM_BYTES : T2_SMEM_BYTES;
+  cfg.dynamicSmemBytes = version == 6 ? T5_SMEM_BYTES : T3_SMEM_BYTES;
   cfg.stream = stm;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;

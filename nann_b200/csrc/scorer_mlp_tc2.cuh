@@ -25,6 +25,7 @@ constexpr int T2_THREADS = 64 + T2_EPI_THREADS;
 constexpr int T2_STAGE = 32768;
 constexpr int T2_NS = 5;
 constexpr int T2_X_BYTES = 65536;
+constexpr int T3_SMEM_BYTES = T2_X_BYTES + T2_NS * T2_STAGE + 3072 /*barriers, tmem slot, hu tile; == 227 KB*/;
 constexpr int T2_SMEM_BYTES = T2_X_BYTES + T2_NS * T2_STAGE + 1024 /*align*/ + 1024 /*barriers, tmem slot, partials*/;
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {

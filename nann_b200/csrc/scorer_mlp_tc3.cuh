@@ -78,12 +78,16 @@ mlp_tc3_kernel(MlpTcArgs p) {
     if (trace && tile_local < 64) trace[tile_local * 48 + ev] = clock64();
   };
   extern __shared__ uint8_t tc_smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
+  // No alignment slack: the kernel has no static shared memory, so the dynamic window starts 1024-aligned.
+  uint8_t* smem = tc_smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* sX = smem;                                   // x tile, later A double buffer (2 x 32 KB)
   uint8_t* sR = smem + T2_X_BYTES;                      // ring
   uint64_t* bars = (uint64_t*)(sR + T2_NS * T2_STAGE);
   uint32_t* tmem_slot = (uint32_t*)(bars + T2Bars::count);
-  float* part = (float*)(bars + T2Bars::count + 1);    // [128] partial sums of the upper column half
+  static_assert(T2Bars::count < 32, "barrier block is 256 B");
+  float* hu_s = (float*)(bars + 32);    // [512] this tile's hoisted layer-1 prefix (per query)
+  float* part = (float*)sX;                            // [128] upper-column-half partial sums; sX is idle in epilogue 2
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t bar0 = smem_u32(bars);
@@ -346,6 +350,12 @@ mlp_tc3_kernel(MlpTcArgs p) {
       fence_proxy_async();
       mbar_arrive(B(T2Bars::x_ready));
       if (tr_thread) TR(tl, 1);
+      {  // hu[q] -> shared (2 KB): the layer-1 epilogue reads it as broadcast LDS instead of L1-missing LDGs
+        const int et = ew * 32 + lane;                   // 0..255
+        const float2 hv = *reinterpret_cast<const float2*>(p.hu + (int64_t)q * MLP_H + et * 2);
+        *reinterpret_cast<float2*>(hu_s + et * 2) = hv;
+        asm volatile("bar.sync 1, %0;" ::"n"(T2_EPI_THREADS) : "memory");
+      }
 
       // ---- while this tile computes: pull the NEXT tile's rows towards L2 (4 x 128-B lines per row)
       {
@@ -360,7 +370,7 @@ mlp_tc3_kernel(MlpTcArgs p) {
       }
 
       // ---- epilogue 1: h1 = relu(D1 + hu) -> (hi, lo) fp16 -> L2 scratch, chunk by chunk
-      const float* huq = p.hu + (int64_t)q * MLP_H;
+      const float* huq = hu_s;
       for (int c = 0; c < 4; ++c) {
         const int b = c & 1;
         mbar_wait(B(T2Bars::d1_full + b), d1f_cnt[b] & 1); ++d1f_cnt[b];
@@ -380,7 +390,8 @@ mlp_tc3_kernel(MlpTcArgs p) {
           const int slab = neuron0 >> 6;
 #pragma unroll
           for (int ch = 0; ch < 4; ++ch) {                      // 8 columns -> one 16-byte chunk per plane
-            const float4 ha = ldg4(huq + neuron0 + ch * 8), hb = ldg4(huq + neuron0 + ch * 8 + 4);
+            const float4 ha = *reinterpret_cast<const float4*>(huq + neuron0 + ch * 8);
+            const float4 hb = *reinterpret_cast<const float4*>(huq + neuron0 + ch * 8 + 4);
             uint32_t hw[4], lw[4];
             bias_relu_split2(v[ch * 8 + 0], v[ch * 8 + 1], make_float2(ha.x, ha.y), hw[0], lw[0]);
             bias_relu_split2(v[ch * 8 + 2], v[ch * 8 + 3], make_float2(ha.z, ha.w), hw[1], lw[1]);
@@ -416,7 +427,8 @@ mlp_tc3_kernel(MlpTcArgs p) {
         auto consume = [&](const uint32_t (&v)[32], int col0) {
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 bb = ldg4(p.b2 + col0 + j4 * 4), ww = ldg4(p.w3 + col0 + j4 * 4);
+            const float4 bb = *reinterpret_cast<const float4*>(&p.b2c[col0 + j4 * 4]);
+            const float4 ww = *reinterpret_cast<const float4*>(&p.w3c[col0 + j4 * 4]);
             float2 z0 = add2(make_float2(__uint_as_float(v[j4 * 4 + 0]), __uint_as_float(v[j4 * 4 + 1])), make_float2(bb.x, bb.y));
             float2 z1 = add2(make_float2(__uint_as_float(v[j4 * 4 + 2]), __uint_as_float(v[j4 * 4 + 3])), make_float2(bb.z, bb.w));
             z0.x = fmaxf(z0.x, 0.f); z0.y = fmaxf(z0.y, 0.f); z1.x = fmaxf(z1.x, 0.f); z1.y = fmaxf(z1.y, 0.f);
