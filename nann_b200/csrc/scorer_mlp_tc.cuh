@@ -97,6 +97,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
   }
 }
+// One lane of a converged warp (CUTLASS's elect_one_sync).  Guarding tcgen05.mma / commit with this inside
+// warp-uniform control flow lets ptxas keep descriptors in uniform registers; an `if (lane == 0)` region made
+// it wrap every UTCHMMA in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loop (~15 instructions per MMA).
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred;
+}
+// lane 0 polls, the warp reconverges: keeps the caller's control flow warp-uniform
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
+  __syncwarp();
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

@@ -137,28 +137,28 @@ mlp_tc3_kernel(MlpTcArgs p) {
 
   if (warp == 0) {
     // =============================== producer ===============================
-    if (lane == 0) {
+    {   // warp-uniform control flow; one elected lane issues the bulk copies (see elect_one())
       uint32_t it = 0;                         // ring stage counter across tiles
       auto ring_load = [&](const void* src) {
         const uint32_t slot = it % T2_NS, ph = (it / T2_NS) & 1;
-        mbar_wait(B(T2Bars::empty + slot), ph ^ 1);          // released by the MMA threads of ALL CTAs of the cluster
-        mbar_expect_tx(B(T2Bars::full + slot), T2_STAGE);
-        if (CL == 1) {
-          bulk_g2s(sR_u + slot * T2_STAGE, src, T2_STAGE, B(T2Bars::full + slot));
-        } else {   // this CTA fetches 1/CL of the stage and multicasts it into every CTA of the cluster
-          constexpr uint32_t part_bytes = T2_STAGE / CL;
-          bulk_g2s_mc(sR_u + slot * T2_STAGE + cta_rank * part_bytes, (const uint8_t*)src + cta_rank * part_bytes,
-                      part_bytes, B(T2Bars::full + slot), (uint16_t)((1u << CL) - 1));
+        mbar_wait_warp(B(T2Bars::empty + slot), ph ^ 1);     // released by the MMA threads of ALL CTAs of the cluster
+        if (elect_one()) {
+          mbar_expect_tx(B(T2Bars::full + slot), T2_STAGE);
+          if (CL == 1) {
+            bulk_g2s(sR_u + slot * T2_STAGE, src, T2_STAGE, B(T2Bars::full + slot));
+          } else {   // this CTA fetches 1/CL of the stage and multicasts it into every CTA of the cluster
+            constexpr uint32_t part_bytes = T2_STAGE / CL;
+            bulk_g2s_mc(sR_u + slot * T2_STAGE + cta_rank * part_bytes, (const uint8_t*)src + cta_rank * part_bytes,
+                        part_bytes, B(T2Bars::full + slot), (uint16_t)((1u << CL) - 1));
+          }
         }
         ++it;
       };
-      int tl = -1;
-      for (int64_t g = g_first; g < n_tiles; g += g_step) {
-        int q, t0, nt;
-        if (!tile_info(g, q, t0, nt)) continue;
-        ++tl;
+      const int64_t my_tiles = (n_tiles > g_first) ? (n_tiles - g_first + g_step - 1) / g_step : 0;
+      for (int64_t tl64 = 0; tl64 < my_tiles; ++tl64) {
+        const int tl = (int)tl64;
         for (int c = 0; c < 4; ++c) {
-          if (c == 0) TR(tl, 32);
+          if (c == 0 && lane == 0) TR(tl, 32);
           ring_load((const uint8_t*)p.W1img + (size_t)c * TC_B_BYTES);
           ring_load((const uint8_t*)p.W1img + (size_t)c * TC_B_BYTES + T2_STAGE);
         }
@@ -169,105 +169,118 @@ mlp_tc3_kernel(MlpTcArgs p) {
             ring_load(w + T2_STAGE);
           }
         }
-        TR(tl, 33);
+        if (lane == 0) TR(tl, 33);
       }
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
-    if (lane == 0) {
+    // The whole warp runs the loops (uniform control flow, uniform-register descriptors); one elected lane
+    // issues the tcgen05 instructions.
+    {
       uint32_t it = 0, a_cnt[2] = {0, 0}, d1e_cnt[2] = {0, 0}, xr_ph = 0, d2e_ph = 1;
       const uint32_t idesc1 = umma_idesc_f16(128, 128), idesc2 = umma_idesc_f16(128, 256);
       auto ring_wait = [&]() -> uint32_t {      // returns the smem address of the next stage
         const uint32_t slot = it % T2_NS, ph = (it / T2_NS) & 1;
-        mbar_wait(B(T2Bars::full + slot), ph);
+        mbar_wait_warp(B(T2Bars::full + slot), ph);
         tc_fence_after();
         return sR_u + slot * T2_STAGE;
       };
-      auto ring_release = [&]() {
+      auto ring_release = [&]() {               // call from the elected lane
         if (CL == 1) tc_commit(B(T2Bars::empty + (it % T2_NS)));
         else tc_commit_mc(B(T2Bars::empty + (it % T2_NS)), (uint16_t)((1u << CL) - 1));
-        ++it;
       };
-      int tl = -1;
-      for (int64_t g = g_first; g < n_tiles; g += g_step) {
-        int q, t0, nt;
-        if (!tile_info(g, q, t0, nt)) continue;
-        ++tl;
-        mbar_wait(B(T2Bars::d2_empty), d2e_ph); d2e_ph ^= 1;      // previous tile's epilogue drained TMEM
-        TR(tl, 2);
-        mbar_wait(B(T2Bars::x_ready), xr_ph); xr_ph ^= 1;         // x tile (hi/lo, swizzled) is in smem
-        TR(tl, 3);
+      const int64_t my_tiles = (n_tiles > g_first) ? (n_tiles - g_first + g_step - 1) / g_step : 0;
+      for (int64_t tl64 = 0; tl64 < my_tiles; ++tl64) {
+        const int tl = (int)tl64;
+        mbar_wait_warp(B(T2Bars::d2_empty), d2e_ph); d2e_ph ^= 1;      // previous tile's epilogue drained TMEM
+        if (lane == 0) TR(tl, 2);
+        mbar_wait_warp(B(T2Bars::x_ready), xr_ph); xr_ph ^= 1;         // x tile (hi/lo, swizzled) is in smem
+        if (lane == 0) TR(tl, 3);
         tc_fence_after();
         // ---- phase 1
         for (int c = 0; c < 4; ++c) {
           const int b = c & 1;
-          mbar_wait(B(T2Bars::d1_empty + b), (d1e_cnt[b] & 1) ^ 1); ++d1e_cnt[b];
+          mbar_wait_warp(B(T2Bars::d1_empty + b), (d1e_cnt[b] & 1) ^ 1); ++d1e_cnt[b];
           tc_fence_after();
           const uint32_t d = tmem + (uint32_t)(b * 128);
           const uint32_t bh = ring_wait();                        // W1 hi(c): [slab0 16 KB][slab1 16 KB]
+          if (elect_one()) {
 #pragma unroll
-          for (int slab = 0; slab < 2; ++slab)
+            for (int slab = 0; slab < 2; ++slab)
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              const uint64_t xh = umma_desc_sw128(sX_u + slab * TC_SLAB_BYTES + ks * 32);
-              const uint64_t xl = umma_desc_sw128(sX_u + (2 + slab) * TC_SLAB_BYTES + ks * 32);
-              const uint64_t wh = umma_desc_sw128(bh + slab * TC_SLAB_BYTES + ks * 32);
-              tc_mma_f16(d, xh, wh, idesc1, (slab | ks) ? 1u : 0u);
-              tc_mma_f16(d, xl, wh, idesc1, 1u);
-            }
-          ring_release();
+              for (int ks = 0; ks < 4; ++ks) {
+                const uint64_t xh = umma_desc_sw128(sX_u + slab * TC_SLAB_BYTES + ks * 32);
+                const uint64_t xl = umma_desc_sw128(sX_u + (2 + slab) * TC_SLAB_BYTES + ks * 32);
+                const uint64_t wh = umma_desc_sw128(bh + slab * TC_SLAB_BYTES + ks * 32);
+                tc_mma_f16(d, xh, wh, idesc1, (slab | ks) ? 1u : 0u);
+                tc_mma_f16(d, xl, wh, idesc1, 1u);
+              }
+            ring_release();
+          }
+          ++it;
           const uint32_t bl = ring_wait();                        // W1 lo(c)
+          if (elect_one()) {
 #pragma unroll
-          for (int slab = 0; slab < 2; ++slab)
+            for (int slab = 0; slab < 2; ++slab)
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              const uint64_t xh = umma_desc_sw128(sX_u + slab * TC_SLAB_BYTES + ks * 32);
-              const uint64_t wl = umma_desc_sw128(bl + slab * TC_SLAB_BYTES + ks * 32);
-              tc_mma_f16(d, xh, wl, idesc1, 1u);
-            }
-          ring_release();
-          tc_commit(B(T2Bars::d1_full + b));
-          TR(tl, 4 + c);
+              for (int ks = 0; ks < 4; ++ks) {
+                const uint64_t xh = umma_desc_sw128(sX_u + slab * TC_SLAB_BYTES + ks * 32);
+                const uint64_t wl = umma_desc_sw128(bl + slab * TC_SLAB_BYTES + ks * 32);
+                tc_mma_f16(d, xh, wl, idesc1, 1u);
+              }
+            ring_release();
+            tc_commit(B(T2Bars::d1_full + b));
+          }
+          ++it;
+          if (lane == 0) TR(tl, 4 + c);
         }
-        tc_commit(B(T2Bars::a_empty + 0));      // x tile fully consumed: both A buffers may be overwritten
-        tc_commit(B(T2Bars::a_empty + 1));
+        if (elect_one()) {
+          tc_commit(B(T2Bars::a_empty + 0));      // x tile fully consumed: both A buffers may be overwritten
+          tc_commit(B(T2Bars::a_empty + 1));
+        }
         // D2 overlaps the D1 buffers: wait until the epilogue drained the last two chunks
-        mbar_wait(B(T2Bars::d1_empty + 0), (d1e_cnt[0] & 1) ^ 1);
-        mbar_wait(B(T2Bars::d1_empty + 1), (d1e_cnt[1] & 1) ^ 1);
+        mbar_wait_warp(B(T2Bars::d1_empty + 0), (d1e_cnt[0] & 1) ^ 1);
+        mbar_wait_warp(B(T2Bars::d1_empty + 1), (d1e_cnt[1] & 1) ^ 1);
         tc_fence_after();
-        TR(tl, 16);
+        if (lane == 0) TR(tl, 16);
         // ---- phase 2
         for (int s = 0; s < 8; ++s) {
           const int b = s & 1;
-          mbar_wait(B(T2Bars::a_full + b), a_cnt[b] & 1); ++a_cnt[b];
-          TR(tl, 17 + s);
+          mbar_wait_warp(B(T2Bars::a_full + b), a_cnt[b] & 1); ++a_cnt[b];
+          if (lane == 0) TR(tl, 17 + s);
           tc_fence_after();
           const uint32_t a_u = sX_u + b * T2_STAGE;               // [hi 16 KB][lo 16 KB]
           for (int h = 0; h < 2; ++h) {
             const uint32_t d = tmem + (uint32_t)(h * 256);
             const uint32_t bh = ring_wait();                      // W2 hi(s,h): [256 rows][64 k]
+            if (elect_one()) {
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              const uint64_t ah = umma_desc_sw128(a_u + ks * 32);
-              const uint64_t al = umma_desc_sw128(a_u + TC_SLAB_BYTES + ks * 32);
-              const uint64_t wh = umma_desc_sw128(bh + ks * 32);
-              tc_mma_f16(d, ah, wh, idesc2, (s | ks) ? 1u : 0u);
-              tc_mma_f16(d, al, wh, idesc2, 1u);
+              for (int ks = 0; ks < 4; ++ks) {
+                const uint64_t ah = umma_desc_sw128(a_u + ks * 32);
+                const uint64_t al = umma_desc_sw128(a_u + TC_SLAB_BYTES + ks * 32);
+                const uint64_t wh = umma_desc_sw128(bh + ks * 32);
+                tc_mma_f16(d, ah, wh, idesc2, (s | ks) ? 1u : 0u);
+                tc_mma_f16(d, al, wh, idesc2, 1u);
+              }
+              ring_release();
             }
-            ring_release();
+            ++it;
             const uint32_t bl = ring_wait();                      // W2 lo(s,h)
+            if (elect_one()) {
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              const uint64_t ah = umma_desc_sw128(a_u + ks * 32);
-              const uint64_t wl = umma_desc_sw128(bl + ks * 32);
-              tc_mma_f16(d, ah, wl, idesc2, 1u);
+              for (int ks = 0; ks < 4; ++ks) {
+                const uint64_t ah = umma_desc_sw128(a_u + ks * 32);
+                const uint64_t wl = umma_desc_sw128(bl + ks * 32);
+                tc_mma_f16(d, ah, wl, idesc2, 1u);
+              }
+              ring_release();
             }
-            ring_release();
+            ++it;
           }
-          if (s < 6) tc_commit(B(T2Bars::a_empty + b));           // slab s consumed -> slab s+2 may load
+          if (s < 6 && elect_one()) tc_commit(B(T2Bars::a_empty + b));   // slab s consumed -> slab s+2 may load
         }
-        tc_commit(B(T2Bars::d2_full));
-        TR(tl, 25);
+        if (elect_one()) tc_commit(B(T2Bars::d2_full));
+        if (lane == 0) TR(tl, 25);
       }
     }
   } else if (warp == 2 + T2_EPI_WARPS) {
