@@ -85,11 +85,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
   unsigned long long t0 = 0;
   for (uint32_t spin = 0; !done; ++spin) {
+#ifdef NANN_MBAR_HINT_NS
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity), "r"((uint32_t)NANN_MBAR_HINT_NS) : "memory");
+#else
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+#endif
     if (!done && (spin & 63) == 63) {
       const unsigned long long now = global_ns();
       if (t0 == 0) t0 = now;
@@ -252,8 +260,9 @@ struct MlpTcArgs {
   // b2 / w3 by value: kernel parameters live in the constant bank, so the layer-2 epilogue reads them with
   // uniform constant loads.  (With ~225 KB of shared memory per CTA the L1 data cache is a few KB: __ldg of
   // these vectors missed to L2 on almost every access and throttled the epilogues.)
-  float b2c[MLP_H];
-  float w3c[MLP_H];
+  int mma_gap;                                    // debug (NANN_TC_GAP): cycles between phase-2 MMA issues
+  alignas(16) float b2c[MLP_H];
+  alignas(16) float w3c[MLP_H];
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -542,6 +551,7 @@ static nann_status mlp_tc_score(nann_scorer* s, const ScoreCall& c, cudaStream_t
   a.n_ptr = c.n_ptr; a.n_fixed = c.n_fixed; a.tiles_per_q = (int)ceil_div(c.max_n, TC_M); a.B = c.B;
   a.hu = c.hu; a.W1img = st->W1img; a.W2img = st->W2img; a.W1img5 = st->W1img5; a.b2 = s->b2; a.w3 = s->w3;
   a.out = c.out; a.out_stride = c.out_stride; a.status = c.status;
+  { const char* g = getenv("NANN_TC_GAP"); a.mma_gap = g ? atoi(g) : 0; }
   memcpy(a.b2c, st->h_b2, sizeof(a.b2c));
   memcpy(a.w3c, st->h_w3, sizeof(a.w3c));
   const int64_t n_tiles = (int64_t)a.B * a.tiles_per_q;
@@ -552,7 +562,8 @@ static nann_status mlp_tc_score(nann_scorer* s, const ScoreCall& c, cudaStream_t
   // 3 = 2 + dense tile list, 4 = 3 as 2-CTA clusters with multicast weight stages,
   // 5 = on-chip h1 hand-off, two layer-2 passes (scorer_mlp_tc5.cuh), 6 = 5 as 2-CTA clusters (multicast)
   static const int version = [] { const char* e = std::getenv("NANN_TC_KERNEL"); return e ? atoi(e) : 3; }();
-  const int grid = (int)std::min<int64_t>(st->n_ctas, n_tiles);
+  static const int cta_cap = [] { const char* e = std::getenv("NANN_TC_CTAS"); return e ? atoi(e) : 1 << 30; }();   // debug
+  const int grid = (int)std::min<int64_t>(std::min(st->n_ctas, cta_cap), n_tiles);
   if (version == 1) { NANN_LAUNCH(mlp_tc_kernel, grid, TC_THREADS, TC_SMEM_BYTES, stm, a); return NANN_OK; }
   if (version == 2) { NANN_LAUNCH(mlp_tc2_kernel, grid, T2_THREADS, T2_SMEM_BYTES, stm, a); return NANN_OK; }
   NANN_LAUNCH(tile_scan_kernel, 1, 1024, 0, stm, c.n_ptr, c.n_fixed, c.status, c.B, c.ws->tile_start);

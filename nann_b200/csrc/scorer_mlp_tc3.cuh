@@ -142,6 +142,7 @@ mlp_tc3_kernel(MlpTcArgs p) {
       auto ring_load = [&](const void* src) {
         const uint32_t slot = it % T2_NS, ph = (it / T2_NS) & 1;
         mbar_wait_warp(B(T2Bars::empty + slot), ph ^ 1);     // released by the MMA threads of ALL CTAs of the cluster
+        if (trace && lane == 0 && it >= 11 * 40 && it < 12 * 40) trace[62 * 48 + (it - 11 * 40)] = clock64();
         if (elect_one()) {
           mbar_expect_tx(B(T2Bars::full + slot), T2_STAGE);
           if (CL == 1) {
@@ -178,12 +179,20 @@ mlp_tc3_kernel(MlpTcArgs p) {
     // issues the tcgen05 instructions.
     {
       uint32_t it = 0, a_cnt[2] = {0, 0}, d1e_cnt[2] = {0, 0}, xr_ph = 0, d2e_ph = 1;
+      long long ring_cyc = 0, afull_cyc = 0;    // debug: cycles this warp waited on the weight ring / on h1 slabs
       const uint32_t idesc1 = umma_idesc_f16(128, 128), idesc2 = umma_idesc_f16(128, 256);
       auto ring_wait = [&]() -> uint32_t {      // returns the smem address of the next stage
         const uint32_t slot = it % T2_NS, ph = (it / T2_NS) & 1;
+        const long long w0 = trace ? clock64() : 0;
         mbar_wait_warp(B(T2Bars::full + slot), ph);
+        if (trace) ring_cyc += clock64() - w0;
+        if (trace && lane == 0 && it >= 11 * 40 && it < 12 * 40) trace[63 * 48 + (it - 11 * 40)] = clock64();
         tc_fence_after();
         return sR_u + slot * T2_STAGE;
+      };
+      const uint32_t mma_gap = (uint32_t)p.mma_gap;
+      auto gap = [&]() {                         // debug knob: minimum spacing between phase-2 MMA issues
+        if (mma_gap) { const uint32_t t0 = (uint32_t)clock(); while ((uint32_t)clock() - t0 < mma_gap) {} }
       };
       auto ring_release = [&]() {               // call from the elected lane
         if (CL == 1) tc_commit(B(T2Bars::empty + (it % T2_NS)));
@@ -204,30 +213,37 @@ mlp_tc3_kernel(MlpTcArgs p) {
           tc_fence_after();
           const uint32_t d = tmem + (uint32_t)(b * 128);
           const uint32_t bh = ring_wait();                        // W1 hi(c): [slab0 16 KB][slab1 16 KB]
+          // Rolled k loops (descriptor += 32 B per k step): the per-MMA operand setup then overlaps the previous
+          // MMA's execution.  Fully unrolled, ptxas front-loads ~40 R2UR moves before the first UTCHMMA of a
+          // stage and the tensor pipe drains meanwhile (the issue queue is only a couple of MMAs deep).
           if (elect_one()) {
-#pragma unroll
-            for (int slab = 0; slab < 2; ++slab)
-#pragma unroll
+#pragma unroll 1
+            for (int slab = 0; slab < 2; ++slab) {
+              uint64_t xh = umma_desc_sw128(sX_u + slab * TC_SLAB_BYTES);
+              uint64_t xl = umma_desc_sw128(sX_u + (2 + slab) * TC_SLAB_BYTES);
+              uint64_t wh = umma_desc_sw128(bh + slab * TC_SLAB_BYTES);
+#pragma unroll 1
               for (int ks = 0; ks < 4; ++ks) {
-                const uint64_t xh = umma_desc_sw128(sX_u + slab * TC_SLAB_BYTES + ks * 32);
-                const uint64_t xl = umma_desc_sw128(sX_u + (2 + slab) * TC_SLAB_BYTES + ks * 32);
-                const uint64_t wh = umma_desc_sw128(bh + slab * TC_SLAB_BYTES + ks * 32);
                 tc_mma_f16(d, xh, wh, idesc1, (slab | ks) ? 1u : 0u);
                 tc_mma_f16(d, xl, wh, idesc1, 1u);
+                xh += 2; xl += 2; wh += 2;
               }
+            }
             ring_release();
           }
           ++it;
           const uint32_t bl = ring_wait();                        // W1 lo(c)
           if (elect_one()) {
-#pragma unroll
-            for (int slab = 0; slab < 2; ++slab)
-#pragma unroll
+#pragma unroll 1
+            for (int slab = 0; slab < 2; ++slab) {
+              uint64_t xh = umma_desc_sw128(sX_u + slab * TC_SLAB_BYTES);
+              uint64_t wl = umma_desc_sw128(bl + slab * TC_SLAB_BYTES);
+#pragma unroll 1
               for (int ks = 0; ks < 4; ++ks) {
-                const uint64_t xh = umma_desc_sw128(sX_u + slab * TC_SLAB_BYTES + ks * 32);
-                const uint64_t wl = umma_desc_sw128(bl + slab * TC_SLAB_BYTES + ks * 32);
                 tc_mma_f16(d, xh, wl, idesc1, 1u);
+                xh += 2; wl += 2;
               }
+            }
             ring_release();
             tc_commit(B(T2Bars::d1_full + b));
           }
@@ -246,7 +262,9 @@ mlp_tc3_kernel(MlpTcArgs p) {
         // ---- phase 2
         for (int s = 0; s < 8; ++s) {
           const int b = s & 1;
+          const long long w1 = trace ? clock64() : 0;
           mbar_wait_warp(B(T2Bars::a_full + b), a_cnt[b] & 1); ++a_cnt[b];
+          if (trace) afull_cyc += clock64() - w1;
           if (lane == 0) TR(tl, 17 + s);
           tc_fence_after();
           const uint32_t a_u = sX_u + b * T2_STAGE;               // [hi 16 KB][lo 16 KB]
@@ -254,24 +272,23 @@ mlp_tc3_kernel(MlpTcArgs p) {
             const uint32_t d = tmem + (uint32_t)(h * 256);
             const uint32_t bh = ring_wait();                      // W2 hi(s,h): [256 rows][64 k]
             if (elect_one()) {
-#pragma unroll
+              uint64_t ah = umma_desc_sw128(a_u), al = umma_desc_sw128(a_u + TC_SLAB_BYTES), wh = umma_desc_sw128(bh);
+#pragma unroll 1
               for (int ks = 0; ks < 4; ++ks) {
-                const uint64_t ah = umma_desc_sw128(a_u + ks * 32);
-                const uint64_t al = umma_desc_sw128(a_u + TC_SLAB_BYTES + ks * 32);
-                const uint64_t wh = umma_desc_sw128(bh + ks * 32);
                 tc_mma_f16(d, ah, wh, idesc2, (s | ks) ? 1u : 0u);
                 tc_mma_f16(d, al, wh, idesc2, 1u);
+                ah += 2; al += 2; wh += 2;
               }
               ring_release();
             }
             ++it;
             const uint32_t bl = ring_wait();                      // W2 lo(s,h)
             if (elect_one()) {
-#pragma unroll
+              uint64_t ah = umma_desc_sw128(a_u), wl = umma_desc_sw128(bl);
+#pragma unroll 1
               for (int ks = 0; ks < 4; ++ks) {
-                const uint64_t ah = umma_desc_sw128(a_u + ks * 32);
-                const uint64_t wl = umma_desc_sw128(bl + ks * 32);
                 tc_mma_f16(d, ah, wl, idesc2, 1u);
+                ah += 2; wl += 2;
               }
               ring_release();
             }
@@ -281,6 +298,8 @@ mlp_tc3_kernel(MlpTcArgs p) {
         }
         if (elect_one()) tc_commit(B(T2Bars::d2_full));
         if (lane == 0) TR(tl, 25);
+        if (trace && lane == 0 && tl < 64) { trace[tl * 48 + 46] = ring_cyc; trace[tl * 48 + 47] = afull_cyc; }
+        ring_cyc = 0; afull_cyc = 0;
       }
     }
   } else if (warp == 2 + T2_EPI_WARPS) {
@@ -294,9 +313,9 @@ mlp_tc3_kernel(MlpTcArgs p) {
       if (!tile_info(g, q, t0, nt)) continue;
       ++tl;
       for (int s = 0; s < 8; ++s) {
-        if ((s & 1) == 0) { mbar_wait(B(T2Bars::h1_done + (s >> 1)), h1_ph); if (lane == 0) TR(tl, 28 + (s >> 1)); }
+        if ((s & 1) == 0) { mbar_wait_warp(B(T2Bars::h1_done + (s >> 1)), h1_ph); if (lane == 0) TR(tl, 28 + (s >> 1)); }
         const int b = s & 1;
-        mbar_wait(B(T2Bars::a_empty + b), a_cnt[b] & 1); ++a_cnt[b];        // x tile / slab s-2 no longer read
+        mbar_wait_warp(B(T2Bars::a_empty + b), a_cnt[b] & 1); ++a_cnt[b];        // x tile / slab s-2 no longer read
         if (lane == 0) TR(tl, 34 + s);
         uint8_t* dst = sX + b * T2_STAGE;
         const uint8_t* src = scratch + (size_t)s * T2_STAGE;
@@ -386,7 +405,7 @@ mlp_tc3_kernel(MlpTcArgs p) {
       const float* huq = hu_s;
       for (int c = 0; c < 4; ++c) {
         const int b = c & 1;
-        mbar_wait(B(T2Bars::d1_full + b), d1f_cnt[b] & 1); ++d1f_cnt[b];
+        mbar_wait_warp(B(T2Bars::d1_full + b), d1f_cnt[b] & 1); ++d1f_cnt[b];
         tc_fence_after();
         if (tr_thread) TR(tl, 8 + c);
         uint32_t va[32], vb[32];
@@ -429,7 +448,7 @@ mlp_tc3_kernel(MlpTcArgs p) {
 
       // ---- epilogue 2: s = sum_j w3[j] * relu(D2[row][j] + b2[j]); each warp of a lane quarter takes
       // 256 of the 512 columns (j ascending inside a half), lower half + upper half
-      mbar_wait(B(T2Bars::d2_full), d2f_ph); d2f_ph ^= 1;
+      mbar_wait_warp(B(T2Bars::d2_full), d2f_ph); d2f_ph ^= 1;
       tc_fence_after();
       if (tr_thread) TR(tl, 26);
       float acc = 0.f;

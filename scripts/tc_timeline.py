@@ -38,4 +38,8 @@ for tile in (10, 11):
     print(f"--- tile {tile} (cycles from event 0)")
     for ev in sorted(names, key=lambda e: t[tile][e]):
         if t[tile][ev]: print(f"{t[tile][ev]-base:9d}  {names[ev]}")
+b11 = t[11][0]
+print("tile 11 ring stages: producer saw slot empty:", [int(x - b11) for x in t[62][:40]])
+print("tile 11 ring stages: mma saw stage full:   ", [int(x - b11) for x in t[63][:40]])
+print("mma warp waits per tile: ring", [int(t[i][46]) for i in range(8, 12)], "a_full", [int(t[i][47]) for i in range(8, 12)])
 print("tile period (cycles):", [int(t[i+1][0]-t[i][0]) for i in range(5, 15)])
