@@ -17,6 +17,20 @@ __device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
                ::"r"(bar), "h"(mask) : "memory");
 }
 
+struct T3Bars {           // mbarrier indices (8 B each) of mlp_tc3_kernel
+  static constexpr int full = 0;        // [5] ring stage filled (TMA complete_tx)
+  static constexpr int empty = 5;       // [5] ring stage consumed (tcgen05.commit)
+  static constexpr int a_full = 10;     // [2] h1 slab in shared memory
+  static constexpr int a_empty = 12;    // [2]
+  static constexpr int x_ready = 14;
+  static constexpr int d1_full = 15;    // [4] layer-1 accumulator chunk c (TMEM columns c*128..) complete
+  static constexpr int d1_empty = 19;   // [4] ... drained by the epilogue
+  static constexpr int h1_done = 23;    // [4]
+  static constexpr int d2_full = 27;
+  static constexpr int d2_empty = 28;
+  static constexpr int count = 29;
+};
+
 // ---- tile list: tiles[g] = (q, t) for every 128-row tile of every live query ------------------------
 __global__ void __launch_bounds__(1024)
 tile_scan_kernel(const int32_t* __restrict__ n_ptr, int n_fixed, const int32_t* __restrict__ status, int B,
@@ -84,8 +98,8 @@ mlp_tc3_kernel(MlpTcArgs p) {
   uint8_t* sX = smem;                                   // x tile, later A double buffer (2 x 32 KB)
   uint8_t* sR = smem + T2_X_BYTES;                      // ring
   uint64_t* bars = (uint64_t*)(sR + T2_NS * T2_STAGE);
-  uint32_t* tmem_slot = (uint32_t*)(bars + T2Bars::count);
-  static_assert(T2Bars::count < 32, "barrier block is 256 B");
+  uint32_t* tmem_slot = (uint32_t*)(bars + T3Bars::count);
+  static_assert(T3Bars::count < 32, "barrier block is 256 B");
   float* hu_s = (float*)(bars + 32);    // [512] this tile's hoisted layer-1 prefix (per query)
   float* part = (float*)sX;                            // [128] upper-column-half partial sums; sX is idle in epilogue 2
 
@@ -94,15 +108,15 @@ mlp_tc3_kernel(MlpTcArgs p) {
   auto B = [&](int idx) { return bar0 + 8u * (uint32_t)idx; };
 
   if (tid == 0) {
-    for (int i = 0; i < T2_NS; ++i) { mbar_init(B(T2Bars::full + i), 1); mbar_init(B(T2Bars::empty + i), CL); }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(B(T2Bars::a_full + i), 1); mbar_init(B(T2Bars::a_empty + i), 1);
-      mbar_init(B(T2Bars::d1_full + i), 1); mbar_init(B(T2Bars::d1_empty + i), T2_EPI_THREADS);
+    for (int i = 0; i < T2_NS; ++i) { mbar_init(B(T3Bars::full + i), 1); mbar_init(B(T3Bars::empty + i), CL); }
+    for (int i = 0; i < 2; ++i) { mbar_init(B(T3Bars::a_full + i), 1); mbar_init(B(T3Bars::a_empty + i), 1); }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(B(T3Bars::d1_full + i), 1); mbar_init(B(T3Bars::d1_empty + i), T2_EPI_THREADS);
+      mbar_init(B(T3Bars::h1_done + i), T2_EPI_THREADS);
     }
-    for (int i = 0; i < 4; ++i) mbar_init(B(T2Bars::h1_done + i), T2_EPI_THREADS);
-    mbar_init(B(T2Bars::x_ready), T2_EPI_THREADS);
-    mbar_init(B(T2Bars::d2_full), 1);
-    mbar_init(B(T2Bars::d2_empty), T2_EPI_THREADS);
+    mbar_init(B(T3Bars::x_ready), T2_EPI_THREADS);
+    mbar_init(B(T3Bars::d2_full), 1);
+    mbar_init(B(T3Bars::d2_empty), T2_EPI_THREADS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -141,16 +155,16 @@ mlp_tc3_kernel(MlpTcArgs p) {
       uint32_t it = 0;                         // ring stage counter across tiles
       auto ring_load = [&](const void* src) {
         const uint32_t slot = it % T2_NS, ph = (it / T2_NS) & 1;
-        mbar_wait_warp(B(T2Bars::empty + slot), ph ^ 1);     // released by the MMA threads of ALL CTAs of the cluster
+        mbar_wait(B(T3Bars::empty + slot), ph ^ 1);     // released by the MMA threads of ALL CTAs of the cluster
         if (trace && lane == 0 && it >= 11 * 40 && it < 12 * 40) trace[62 * 48 + (it - 11 * 40)] = clock64();
         if (elect_one()) {
-          mbar_expect_tx(B(T2Bars::full + slot), T2_STAGE);
+          mbar_expect_tx(B(T3Bars::full + slot), T2_STAGE);
           if (CL == 1) {
-            bulk_g2s(sR_u + slot * T2_STAGE, src, T2_STAGE, B(T2Bars::full + slot));
+            bulk_g2s(sR_u + slot * T2_STAGE, src, T2_STAGE, B(T3Bars::full + slot));
           } else {   // this CTA fetches 1/CL of the stage and multicasts it into every CTA of the cluster
             constexpr uint32_t part_bytes = T2_STAGE / CL;
             bulk_g2s_mc(sR_u + slot * T2_STAGE + cta_rank * part_bytes, (const uint8_t*)src + cta_rank * part_bytes,
-                        part_bytes, B(T2Bars::full + slot), (uint16_t)((1u << CL) - 1));
+                        part_bytes, B(T3Bars::full + slot), (uint16_t)((1u << CL) - 1));
           }
         }
         ++it;
@@ -178,13 +192,13 @@ mlp_tc3_kernel(MlpTcArgs p) {
     // The whole warp runs the loops (uniform control flow, uniform-register descriptors); one elected lane
     // issues the tcgen05 instructions.
     {
-      uint32_t it = 0, a_cnt[2] = {0, 0}, d1e_cnt[2] = {0, 0}, xr_ph = 0, d2e_ph = 1;
+      uint32_t it = 0, a_cnt[2] = {0, 0}, d1e_ph = 0, xr_ph = 0, d2e_ph = 1;
       long long ring_cyc = 0, afull_cyc = 0;    // debug: cycles this warp waited on the weight ring / on h1 slabs
       const uint32_t idesc1 = umma_idesc_f16(128, 128), idesc2 = umma_idesc_f16(128, 256);
       auto ring_wait = [&]() -> uint32_t {      // returns the smem address of the next stage
         const uint32_t slot = it % T2_NS, ph = (it / T2_NS) & 1;
         const long long w0 = trace ? clock64() : 0;
-        mbar_wait_warp(B(T2Bars::full + slot), ph);
+        mbar_wait(B(T3Bars::full + slot), ph);
         if (trace) ring_cyc += clock64() - w0;
         if (trace && lane == 0 && it >= 11 * 40 && it < 12 * 40) trace[63 * 48 + (it - 11 * 40)] = clock64();
         tc_fence_after();
@@ -195,22 +209,22 @@ mlp_tc3_kernel(MlpTcArgs p) {
         if (mma_gap) { const uint32_t t0 = (uint32_t)clock(); while ((uint32_t)clock() - t0 < mma_gap) {} }
       };
       auto ring_release = [&]() {               // call from the elected lane
-        if (CL == 1) tc_commit(B(T2Bars::empty + (it % T2_NS)));
-        else tc_commit_mc(B(T2Bars::empty + (it % T2_NS)), (uint16_t)((1u << CL) - 1));
+        if (CL == 1) tc_commit(B(T3Bars::empty + (it % T2_NS)));
+        else tc_commit_mc(B(T3Bars::empty + (it % T2_NS)), (uint16_t)((1u << CL) - 1));
       };
       const int64_t my_tiles = (n_tiles > g_first) ? (n_tiles - g_first + g_step - 1) / g_step : 0;
       for (int64_t tl64 = 0; tl64 < my_tiles; ++tl64) {
         const int tl = (int)tl64;
-        mbar_wait_warp(B(T2Bars::d2_empty), d2e_ph); d2e_ph ^= 1;      // previous tile's epilogue drained TMEM
+        mbar_wait(B(T3Bars::d2_empty), d2e_ph); d2e_ph ^= 1;      // previous tile's epilogue drained TMEM
         if (lane == 0) TR(tl, 2);
-        mbar_wait_warp(B(T2Bars::x_ready), xr_ph); xr_ph ^= 1;         // x tile (hi/lo, swizzled) is in smem
+        mbar_wait(B(T3Bars::x_ready), xr_ph); xr_ph ^= 1;         // x tile (hi/lo, swizzled) is in smem
         if (lane == 0) TR(tl, 3);
         tc_fence_after();
         // ---- phase 1
         for (int c = 0; c < 4; ++c) {
-          const int b = c & 1;
-          mbar_wait_warp(B(T2Bars::d1_empty + b), (d1e_cnt[b] & 1) ^ 1); ++d1e_cnt[b];
-          tc_fence_after();
+          // four D1 chunks, one TMEM column range each (free since d2_empty): the layer-1 MMAs never wait for
+          // the epilogue, which trails one chunk behind
+          const int b = c;
           const uint32_t d = tmem + (uint32_t)(b * 128);
           const uint32_t bh = ring_wait();                        // W1 hi(c): [slab0 16 KB][slab1 16 KB]
           // Rolled k loops (descriptor += 32 B per k step): the per-MMA operand setup then overlaps the previous
@@ -245,25 +259,25 @@ mlp_tc3_kernel(MlpTcArgs p) {
               }
             }
             ring_release();
-            tc_commit(B(T2Bars::d1_full + b));
+            tc_commit(B(T3Bars::d1_full + b));
           }
           ++it;
           if (lane == 0) TR(tl, 4 + c);
         }
         if (elect_one()) {
-          tc_commit(B(T2Bars::a_empty + 0));      // x tile fully consumed: both A buffers may be overwritten
-          tc_commit(B(T2Bars::a_empty + 1));
+          tc_commit(B(T3Bars::a_empty + 0));      // x tile fully consumed: both A buffers may be overwritten
+          tc_commit(B(T3Bars::a_empty + 1));
         }
         // D2 overlaps the D1 buffers: wait until the epilogue drained the last two chunks
-        mbar_wait_warp(B(T2Bars::d1_empty + 0), (d1e_cnt[0] & 1) ^ 1);
-        mbar_wait_warp(B(T2Bars::d1_empty + 1), (d1e_cnt[1] & 1) ^ 1);
+        for (int i = 0; i < 4; ++i) mbar_wait(B(T3Bars::d1_empty + i), d1e_ph);
+        d1e_ph ^= 1;
         tc_fence_after();
         if (lane == 0) TR(tl, 16);
         // ---- phase 2
         for (int s = 0; s < 8; ++s) {
           const int b = s & 1;
           const long long w1 = trace ? clock64() : 0;
-          mbar_wait_warp(B(T2Bars::a_full + b), a_cnt[b] & 1); ++a_cnt[b];
+          mbar_wait(B(T3Bars::a_full + b), a_cnt[b] & 1); ++a_cnt[b];
           if (trace) afull_cyc += clock64() - w1;
           if (lane == 0) TR(tl, 17 + s);
           tc_fence_after();
@@ -294,9 +308,9 @@ mlp_tc3_kernel(MlpTcArgs p) {
             }
             ++it;
           }
-          if (s < 6 && elect_one()) tc_commit(B(T2Bars::a_empty + b));   // slab s consumed -> slab s+2 may load
+          if (s < 6 && elect_one()) tc_commit(B(T3Bars::a_empty + b));   // slab s consumed -> slab s+2 may load
         }
-        if (elect_one()) tc_commit(B(T2Bars::d2_full));
+        if (elect_one()) tc_commit(B(T3Bars::d2_full));
         if (lane == 0) TR(tl, 25);
         if (trace && lane == 0 && tl < 64) { trace[tl * 48 + 46] = ring_cyc; trace[tl * 48 + 47] = afull_cyc; }
         ring_cyc = 0; afull_cyc = 0;
@@ -313,9 +327,9 @@ mlp_tc3_kernel(MlpTcArgs p) {
       if (!tile_info(g, q, t0, nt)) continue;
       ++tl;
       for (int s = 0; s < 8; ++s) {
-        if ((s & 1) == 0) { mbar_wait_warp(B(T2Bars::h1_done + (s >> 1)), h1_ph); if (lane == 0) TR(tl, 28 + (s >> 1)); }
+        if ((s & 1) == 0) { mbar_wait(B(T3Bars::h1_done + (s >> 1)), h1_ph); if (lane == 0) TR(tl, 28 + (s >> 1)); }
         const int b = s & 1;
-        mbar_wait_warp(B(T2Bars::a_empty + b), a_cnt[b] & 1); ++a_cnt[b];        // x tile / slab s-2 no longer read
+        mbar_wait(B(T3Bars::a_empty + b), a_cnt[b] & 1); ++a_cnt[b];        // x tile / slab s-2 no longer read
         if (lane == 0) TR(tl, 34 + s);
         uint8_t* dst = sX + b * T2_STAGE;
         const uint8_t* src = scratch + (size_t)s * T2_STAGE;
@@ -331,7 +345,7 @@ mlp_tc3_kernel(MlpTcArgs p) {
         asm volatile("cp.async.wait_all;" ::: "memory");
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) mbar_arrive(B(T2Bars::a_full + b));
+        if (lane == 0) mbar_arrive(B(T3Bars::a_full + b));
       }
       h1_ph ^= 1;
     }
@@ -342,7 +356,7 @@ mlp_tc3_kernel(MlpTcArgs p) {
     const int col_half = ew >> 2;             // which half of the columns this warp's epilogues cover
     const int row = lane_q * 32 + lane;
     constexpr int ROWS_PER_WARP = TC_M / T2_EPI_WARPS;   // 16
-    uint32_t d1f_cnt[2] = {0, 0}, d2f_ph = 0;
+    uint32_t d1f_ph = 0, d2f_ph = 0;
     auto row_index = [&](int q, int t0, int nt, int r) -> long long {
       const int cc = r < nt ? r : 0;          // pad with the tile's first row (scores not written)
       return p.ids ? (long long)p.ids[(int64_t)q * p.ids_stride + t0 + cc] : ((long long)q * p.rows_stride + t0 + cc);
@@ -380,7 +394,7 @@ mlp_tc3_kernel(MlpTcArgs p) {
         }
       }
       fence_proxy_async();
-      mbar_arrive(B(T2Bars::x_ready));
+      mbar_arrive(B(T3Bars::x_ready));
       if (tr_thread) TR(tl, 1);
       {  // hu[q] -> shared (2 KB): the layer-1 epilogue reads it as broadcast LDS instead of L1-missing LDGs
         const int et = ew * 32 + lane;                   // 0..255
@@ -404,8 +418,8 @@ mlp_tc3_kernel(MlpTcArgs p) {
       // ---- epilogue 1: h1 = relu(D1 + hu) -> (hi, lo) fp16 -> L2 scratch, chunk by chunk
       const float* huq = hu_s;
       for (int c = 0; c < 4; ++c) {
-        const int b = c & 1;
-        mbar_wait_warp(B(T2Bars::d1_full + b), d1f_cnt[b] & 1); ++d1f_cnt[b];
+        const int b = c;
+        mbar_wait(B(T3Bars::d1_full + b), d1f_ph);
         tc_fence_after();
         if (tr_thread) TR(tl, 8 + c);
         uint32_t va[32], vb[32];
@@ -439,51 +453,56 @@ mlp_tc3_kernel(MlpTcArgs p) {
         }
         if (tr_thread && c == 1) TR(tl, 43);
         tc_fence_before();
-        mbar_arrive(B(T2Bars::d1_empty + b));     // D1[b] may be overwritten
+        mbar_arrive(B(T3Bars::d1_empty + b));     // D1[b] may be overwritten
         __threadfence_block();
         if (tr_thread && c == 1) TR(tl, 44);                     // scratch stores before the arrive; the loader reads them with cp.async
-        mbar_arrive(B(T2Bars::h1_done + c));
+        mbar_arrive(B(T3Bars::h1_done + c));
         if (tr_thread) TR(tl, 12 + c);
       }
 
+      d1f_ph ^= 1;
+
       // ---- epilogue 2: s = sum_j w3[j] * relu(D2[row][j] + b2[j]); each warp of a lane quarter takes
       // 256 of the 512 columns (j ascending inside a half), lower half + upper half
-      mbar_wait_warp(B(T2Bars::d2_full), d2f_ph); d2f_ph ^= 1;
+      mbar_wait(B(T3Bars::d2_full), d2f_ph); d2f_ph ^= 1;
       tc_fence_after();
       if (tr_thread) TR(tl, 26);
       float acc = 0.f;
-      {
-        const uint32_t tbase = tmem + ((uint32_t)(lane_q * 32) << 16) + (uint32_t)(col_half * 256);
+      // The column half is a compile-time constant inside each copy, so b2 / w3 are read as constant-bank
+      // operands of the FADD / FFMA themselves (a runtime half needed an LDC per pair and stalled on the MIO queue).
+      auto epi2 = [&](auto colh_c) {
+        constexpr int CH = decltype(colh_c)::value;
+        const uint32_t tbase = tmem + ((uint32_t)(lane_q * 32) << 16) + (uint32_t)(CH * 256);
         uint32_t v0[32], v1[32];
         float2 acc2 = make_float2(0.f, 0.f);
-        auto consume = [&](const uint32_t (&v)[32], int col0) {
+        auto consume = [&](const uint32_t (&v)[32], auto col0_c) {
+          constexpr int col0 = decltype(col0_c)::value;
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 bb = *reinterpret_cast<const float4*>(&p.b2c[col0 + j4 * 4]);
-            const float4 ww = *reinterpret_cast<const float4*>(&p.w3c[col0 + j4 * 4]);
-            float2 z0 = add2(make_float2(__uint_as_float(v[j4 * 4 + 0]), __uint_as_float(v[j4 * 4 + 1])), make_float2(bb.x, bb.y));
-            float2 z1 = add2(make_float2(__uint_as_float(v[j4 * 4 + 2]), __uint_as_float(v[j4 * 4 + 3])), make_float2(bb.z, bb.w));
-            z0.x = fmaxf(z0.x, 0.f); z0.y = fmaxf(z0.y, 0.f); z1.x = fmaxf(z1.x, 0.f); z1.y = fmaxf(z1.y, 0.f);
-            acc2 = fma2(make_float2(ww.x, ww.y), z0, acc2);
-            acc2 = fma2(make_float2(ww.z, ww.w), z1, acc2);
+          for (int j2 = 0; j2 < 16; ++j2) {
+            float2 z = add2(make_float2(__uint_as_float(v[j2 * 2]), __uint_as_float(v[j2 * 2 + 1])),
+                            make_float2(p.b2c[col0 + j2 * 2], p.b2c[col0 + j2 * 2 + 1]));
+            z.x = fmaxf(z.x, 0.f); z.y = fmaxf(z.y, 0.f);
+            acc2 = fma2(make_float2(p.w3c[col0 + j2 * 2], p.w3c[col0 + j2 * 2 + 1]), z, acc2);
           }
         };
         tc_ld32_nowait(tbase, v0);
         tc_ld_wait_dep(v0);
-#pragma unroll
-        for (int pp = 0; pp < 4; ++pp) {        // 8 blocks of 32 columns, the next one in flight while one is consumed
-          tc_ld32_nowait(tbase + (uint32_t)((2 * pp + 1) * 32), v1);
-          consume(v0, col_half * 256 + (2 * pp) * 32);
-          tc_ld_wait_dep(v1);
-          if (pp < 3) tc_ld32_nowait(tbase + (uint32_t)((2 * pp + 2) * 32), v0);
-          consume(v1, col_half * 256 + (2 * pp + 1) * 32);
-          if (pp < 3) tc_ld_wait_dep(v0);
-        }
+        // 8 blocks of 32 columns, the next one in flight while one is consumed
+#define NANN_EPI2_STEP(PP)                                                                      \
+        tc_ld32_nowait(tbase + (uint32_t)((2 * PP + 1) * 32), v1);                              \
+        consume(v0, std::integral_constant<int, CH * 256 + (2 * PP) * 32>{});                   \
+        tc_ld_wait_dep(v1);                                                                     \
+        if (PP < 3) tc_ld32_nowait(tbase + (uint32_t)((2 * PP + 2) * 32), v0);                  \
+        consume(v1, std::integral_constant<int, CH * 256 + (2 * PP + 1) * 32>{});               \
+        if (PP < 3) tc_ld_wait_dep(v0);
+        NANN_EPI2_STEP(0) NANN_EPI2_STEP(1) NANN_EPI2_STEP(2) NANN_EPI2_STEP(3)
+#undef NANN_EPI2_STEP
         acc = acc2.x + acc2.y;
-      }
+      };
+      if (col_half == 0) epi2(std::integral_constant<int, 0>{}); else epi2(std::integral_constant<int, 1>{});
       if (tr_thread) TR(tl, 45);
       tc_fence_before();
-      mbar_arrive(B(T2Bars::d2_empty));           // TMEM is free for the next tile's phase 1
+      mbar_arrive(B(T3Bars::d2_empty));           // TMEM is free for the next tile's phase 1
       if (col_half == 1) part[row] = acc;
       asm volatile("bar.sync 1, %0;" ::"n"(T2_EPI_THREADS) : "memory");
       if (col_half == 0 && row < nt) p.out[(int64_t)q * p.out_stride + t0 + row] = acc + part[row];
