@@ -243,6 +243,8 @@ def run_b200(args, T, rank, world, local_rank):
     extra = {}
     try:
         n_eval = min(args.eval_queries, B)
+        if n_eval <= 0:
+            raise RuntimeError("recall evaluation disabled (--eval-queries 0)")
         res = step_e2e(0)
         got_ids = (res[1] if world > 1 else res["ids"])[:n_eval]
         emb_t = torch.from_numpy(full).to(dev)          # whole corpus (== this shard when world == 1)
@@ -314,10 +316,10 @@ def run_b200(args, T, rank, world, local_rank):
         "clocks": clk.summary(),
         "roofline": {
             "kernel": "mlp_exact_kernel (fused row gather + 2x512 MLP, fp32 FFMA)" if args.precision == "exact"
-                      else "mlp_tc_kernel (fused row gather + 2x512 MLP, tcgen05 fp16-split)",
+                      else "mlp_tc3_kernel (fused row gather + 2x512 MLP, tcgen05 fp16 hi/lo split)",
             "bound": "tensor", "achieved": ach_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
             "frac": ach_tf / pk["tf_sustained"], "peak_source": f"bf16 dense sustained, of {pk['source']}",
-            "traffic": None,
+            "traffic": _ncu_traffic(args.precision),
             "algorithmic_flops_per_row": 2 * MAC_PER_ROW, "rows_per_launch": rows / n_score,
             "avg_launch_ms": score_ms / n_score,
             "gather_GBps_inside_kernel": rows * ROW_BYTES / (score_ms / 1000.0) / 1e9 if score_ms > 0 else 0.0,
@@ -329,6 +331,15 @@ def run_b200(args, T, rank, world, local_rank):
     }
     out.update(extra)
     return out
+
+
+def _ncu_traffic(precision):
+    """DRAM bytes of one launch of the dominant kernel, from the committed `ncu --set full` capture (profiles/)."""
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic.json")) as f:
+            return json.load(f)[precision]["dram_bytes_per_launch"]
+    except Exception:
+        return None
 
 
 def main():
