@@ -33,6 +33,9 @@ if os.environ.get("NANN_TC_KERNEL", "3") in ("5", "6"):
     for h in range(2):
         for c in range(8):
             names[4 + h * 8 + c] = f"A slab h{h} c{c} written"; names[26 + h * 8 + c] = f"mma P2 h{h} c{c} issued"
+if os.environ.get("NANN_TC_KERNEL", "3") == "7":
+    names = {0: "epi iter start", 3: "mma iter start", 4: "mma L1c0 issued", 5: "mma L1c1 issued", 6: "mma pass0 issued", 7: "mma pass1 issued",
+             8: "epi epi1c0 done", 9: "epi epi2h0 done", 10: "epi epi1c1 done", 11: "epi gather(next) done", 12: "epi epi2h1+finish done"}
 for tile in (10, 11):
     base = t[tile][0]
     print(f"--- tile {tile} (cycles from event 0)")
