@@ -36,6 +36,10 @@ if os.environ.get("NANN_TC_KERNEL", "3") in ("5", "6"):
 if os.environ.get("NANN_TC_KERNEL", "3") == "7":
     names = {0: "epi iter start", 3: "mma iter start", 4: "mma L1c0 issued", 5: "mma L1c1 issued", 6: "mma pass0 issued", 7: "mma pass1 issued",
              8: "epi epi1c0 done", 9: "epi epi2h0 done", 10: "epi epi1c1 done", 11: "epi gather(next) done", 12: "epi epi2h1+finish done"}
+if os.environ.get("NANN_TC_KERNEL", "3") == "8":
+    names = {0: "mma tile start", 1: "mma x units issued (d1_full committed)", 2: "mma d2_empty ok", 3: "mma unit 2 issued", 4: "mma unit 3 issued",
+             5: "mma unit 4 issued", 6: "mma unit 5 issued", 7: "mma d2 committed", 8: "epi iter start", 9: "epi d1_full ok", 10: "epi epi1 done",
+             11: "epi gather(next) loads issued", 12: "epi x(next) written", 13: "epi d2_full ok", 14: "epi tile done"}
 for tile in (10, 11):
     base = t[tile][0]
     print(f"--- tile {tile} (cycles from event 0)")
