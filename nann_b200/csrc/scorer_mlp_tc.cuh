@@ -611,7 +611,7 @@ static nann_status mlp_tc_score(nann_scorer* s, const ScoreCall& c, cudaStream_t
   // 3 = 2 + dense tile list, 4 = 3 as 2-CTA clusters with multicast weight stages,
   // 7 = two tiles in flight (layer 1 of tile i overlaps layer 2 of tile i-1, scorer_mlp_tc7.cuh),
   // 5 = on-chip h1 hand-off, two layer-2 passes (scorer_mlp_tc5.cuh), 6 = 5 as 2-CTA clusters (multicast)
-  static const int version = [] { const char* e = std::getenv("NANN_TC_KERNEL"); return e ? atoi(e) : 3; }();
+  static const int version = [] { const char* e = std::getenv("NANN_TC_KERNEL"); return e ? atoi(e) : 8; }();
   static const int cta_cap = [] { const char* e = std::getenv("NANN_TC_CTAS"); return e ? atoi(e) : 1 << 30; }();   // debug
   const int grid = (int)std::min<int64_t>(std::min(st->n_ctas, cta_cap), n_tiles);
   if (version == 1) { NANN_LAUNCH(mlp_tc_kernel, grid, TC_THREADS, TC_SMEM_BYTES, stm, a); return NANN_OK; }

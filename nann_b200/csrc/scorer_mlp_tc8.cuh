@@ -28,8 +28,11 @@
 
 namespace nann {
 
-constexpr int T8_NA = 3;                                // A-slab ring slots (32 KB: [hi 16 KB][lo 16 KB])
-constexpr int T8_NW = 4;                                // weight ring stages (32 KB)
+#ifndef NANN_T8_NA
+#define NANN_T8_NA 4
+#endif
+constexpr int T8_NA = NANN_T8_NA;                       // A-slab ring slots (32 KB: [hi 16 KB][lo 16 KB])
+constexpr int T8_NW = 7 - T8_NA;                        // weight ring stages (32 KB)
 constexpr int T8_UNITS = 10;                            // units per tile
 constexpr int T8_THREADS = 64 + T2_EPI_THREADS;         // 320
 constexpr int T8_SMEM_BYTES = (T8_NA + T8_NW) * T2_STAGE + 3072;
@@ -37,18 +40,18 @@ constexpr int T8_IMG_BYTES_PER_RANK = T8_UNITS * 2 * T2_STAGE;   // 640 KB
 static_assert(T8_SMEM_BYTES <= 232448, "shared memory budget");
 
 struct T8Bars {
-  static constexpr int w_full = 0;      // [4]
-  static constexpr int w_empty = 4;     // [4]
-  static constexpr int a_full = 8;      // [3]  128 thread arrivals (x slabs: local gather; h1 slabs: the owner CTA)
+  static constexpr int w_full = 0;              // [NW]
+  static constexpr int w_empty = T8_NW;         // [NW]
+  static constexpr int a_full = 2 * T8_NW;      // [NA]  one arrival (+ 32 KB of complete_tx when the slab comes from the peer)
   // [3][2]  2 arrivals: multicast commit of both CTAs' MMA warps.  TWO barriers per slot, alternating by use: the
   // producers of a slot's use k are not the same threads every time, so a thread can come to its wait one phase
   // "early" (the peer has not yet consumed the use before last) and a single parity bit would let it through.
-  static constexpr int a_empty = 11;
-  static constexpr int d1_full = 17;
-  static constexpr int d1_empty = 18;   // 256
-  static constexpr int d2_full = 19;
-  static constexpr int d2_empty = 20;   // 256
-  static constexpr int count = 21;
+  static constexpr int a_empty = 2 * T8_NW + T8_NA;
+  static constexpr int d1_full = a_empty + 2 * T8_NA;
+  static constexpr int d1_empty = d1_full + 1;   // 256
+  static constexpr int d2_full = d1_full + 2;
+  static constexpr int d2_empty = d1_full + 3;   // 256
+  static constexpr int count = d1_full + 4;
 };
 // barrier index / parity a producer of unit n waits on before overwriting the slot (n >= T8_NA)
 __device__ __forceinline__ int t8_aempty_idx(uint32_t n) { return T8Bars::a_empty + (int)(n % T8_NA) * 2 + (int)((n / T8_NA - 1) & 1); }
@@ -102,7 +105,7 @@ mlp_tc8_kernel(MlpTcArgs p) {
   const uint32_t peer = rank ^ 1u;
   long long* const trace = (blockIdx.x == 0) ? p.trace : nullptr;
   auto TR = [&](int it_local, int ev) {
-    if (trace && it_local < 64) trace[it_local * 48 + ev] = clock64();
+    if (trace && it_local < 60) trace[it_local * 48 + ev] = clock64();
   };
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* smem = tc_smem_raw;
@@ -182,18 +185,24 @@ mlp_tc8_kernel(MlpTcArgs p) {
       tc_fence_after();
       return sW_u + slot * T2_STAGE;
     };
-    // D[128 x 256] (+)= A[128 x 64] (hi,lo) * W[256 x 64]^T (hi,lo): stage "hi" 8 MMAs, stage "lo" 4 MMAs
+    // D[128 x 256] (+)= A[128 x 64] (hi,lo) * W[256 x 64]^T (hi,lo): stage "hi" 8 MMAs, stage "lo" 4 MMAs.
+    // (Waiting for the NEXT unit's barriers before the last MMAs of this one -- to hide the poll latency behind
+    // queued MMAs -- was measured slower: the kernel is bound by shared-memory bandwidth, not by issue gaps.)
     auto unit = [&](uint32_t d, uint32_t first) {
       const uint32_t slot = n % T8_NA;
       {
         const long long w0 = trace ? clock64() : 0;
-        mbar_wait_cluster(B(T8Bars::a_full + slot), (n / T8_NA) & 1);
+        // CTA-scope acquire: the slab is read by the tensor core (async proxy), never by this warp
+        mbar_wait(B(T8Bars::a_full + slot), (n / T8_NA) & 1);
         if (trace) afull_cyc += clock64() - w0;
       }
-      fence_proxy_async();
       tc_fence_after();
+      const bool st11 = trace && lane == 0 && n >= 11 * T8_UNITS && n < 12 * T8_UNITS;   // debug: unit stamps of tile 11
+      long long* const st = trace + 60 * 48 + (st11 ? (n - 11 * T8_UNITS) * 4 : 0);      // rows 60.. (tiles >= 60 do not stamp)
+      if (st11) st[0] = clock64();
       const uint32_t a_hi = sA_u + slot * T2_STAGE, a_lo = a_hi + TC_SLAB_BYTES;
       const uint32_t bh = ring_wait();
+      if (st11) st[1] = clock64();
       if (elect_one()) {
         uint64_t ah = umma_desc_sw128(a_hi), al = umma_desc_sw128(a_lo), wh = umma_desc_sw128(bh);
 #pragma unroll 1
@@ -206,6 +215,7 @@ mlp_tc8_kernel(MlpTcArgs p) {
       }
       ++it;
       const uint32_t bl = ring_wait();
+      if (st11) st[2] = clock64();
       if (elect_one()) {
         uint64_t ah = umma_desc_sw128(a_hi), wl = umma_desc_sw128(bl);
 #pragma unroll 1
@@ -216,6 +226,7 @@ mlp_tc8_kernel(MlpTcArgs p) {
         tc_commit(B(T8Bars::w_empty + (it % T8_NW)));
         tc_commit_mc(B(T8Bars::a_empty + slot * 2 + ((n / T8_NA) & 1)), (uint16_t)3);   // slab consumed: tell the producers of BOTH CTAs
       }
+      if (st11) st[3] = clock64();
       ++it;
       ++n;
     };
@@ -235,7 +246,7 @@ mlp_tc8_kernel(MlpTcArgs p) {
       }
       if (elect_one()) tc_commit(B(T8Bars::d2_full));
       if (lane == 0) TR(i, 7);
-      if (trace && lane == 0 && i < 64) { trace[i * 48 + 46] = ring_cyc; trace[i * 48 + 47] = afull_cyc; }
+      if (trace && lane == 0 && i < 60) { trace[i * 48 + 46] = ring_cyc; trace[i * 48 + 47] = afull_cyc; }
       ring_cyc = 0; afull_cyc = 0;
     }
   } else {
@@ -290,60 +301,55 @@ mlp_tc8_kernel(MlpTcArgs p) {
         mbar_arrive(B(T8Bars::a_full + (n0 + 1) % T8_NA));
       }
     };
-    // ---- epilogue 1 of tile j: this warp's two slabs (own neurons col_half*128 + jj*64 ..), local + remote
+    // ---- epilogue 1 of tile j: ALL eight warps build every slab (own neurons js*64 ..: this warp's 32 rows x the
+    // 32 columns of its col_half), so a slab is ready one block-time after the previous one; local + peer copy
     auto epi1 = [&](int j) {
       mbar_wait(B(T8Bars::d1_full), j & 1);
       tc_fence_after();
       if (tr_thread) TR(j, 9);
       uint32_t va[32], vb[32];
-      const uint32_t tb = tmem_d1 + t_lane + (uint32_t)(col_half * 128);
+      const uint32_t tb = tmem_d1 + t_lane + (uint32_t)(col_half * 32);
       tc_ld32_nowait(tb, va);
-#pragma unroll
-      for (int jj = 0; jj < 2; ++jj) {
-        const int js = col_half * 2 + jj;                                  // own slab 0..3
+      auto slab = [&](uint32_t (&v)[32], uint32_t (&vnext)[32], int js) {
         const uint32_t n = (uint32_t)j * T8_UNITS + 2 + 2 * js + rank;     // its unit number
         const uint32_t slot = n % T8_NA;
         if (n >= T8_NA) mbar_wait(B(t8_aempty_idx(n)), t8_aempty_par(n));  // both CTAs consumed the slot's previous slab
         uint8_t* dl = sA + slot * T2_STAGE;
-        const uint32_t dr = rA_u + slot * T2_STAGE;
-        auto block = [&](const uint32_t (&v)[32], int blk) {               // 32 columns = chunks blk*4 .. blk*4+3
-          const int neuron0 = js * 64 + blk * 32;                          // own neuron index
+        tc_ld_wait_dep(v);
+        if (js < 3) tc_ld32_nowait(tb + (uint32_t)((js + 1) * 64), vnext);
+        else { tc_fence_before(); mbar_arrive(B(T8Bars::d1_empty)); }      // this thread's last read of D1 has landed
+        const int neuron0 = js * 64 + col_half * 32;                       // own neuron index of v[0]
 #pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
-            const float4 ha = *reinterpret_cast<const float4*>(hu_s + neuron0 + ch * 8);
-            const float4 hb = *reinterpret_cast<const float4*>(hu_s + neuron0 + ch * 8 + 4);
-            uint32_t hw[4], lw[4];
-            bias_relu_split2(v[ch * 8 + 0], v[ch * 8 + 1], make_float2(ha.x, ha.y), hw[0], lw[0]);
-            bias_relu_split2(v[ch * 8 + 2], v[ch * 8 + 3], make_float2(ha.z, ha.w), hw[1], lw[1]);
-            bias_relu_split2(v[ch * 8 + 4], v[ch * 8 + 5], make_float2(hb.x, hb.y), hw[2], lw[2]);
-            bias_relu_split2(v[ch * 8 + 6], v[ch * 8 + 7], make_float2(hb.z, hb.w), hw[3], lw[3]);
-            const uint32_t off = sw128_chunk_off(row, blk * 4 + ch);
-            const uint4 hv = make_uint4(hw[0], hw[1], hw[2], hw[3]), lv = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-            *reinterpret_cast<uint4*>(dl + off) = hv;
-            *reinterpret_cast<uint4*>(dl + TC_SLAB_BYTES + off) = lv;
-          }
-        };
-        tc_ld_wait_dep(va);
-        tc_ld32_nowait(tb + (uint32_t)(jj * 64 + 32), vb);
-        block(va, 0);
-        tc_ld_wait_dep(vb);
-        if (jj == 0) tc_ld32_nowait(tb + 64, va);
-        block(vb, 1);
-        // the slab is complete in THIS CTA's slot once the four warps of the group are here; one thread publishes it
-        // locally and ships the 32 KB to the peer's slot with one DSMEM bulk copy (thread-level st.shared::cluster
-        // stores, 16 B per lane into 32 different rows, ran at ~9 B/clk and starved both MMA warps)
+        for (int ch = 0; ch < 4; ++ch) {
+          const float4 ha = *reinterpret_cast<const float4*>(hu_s + neuron0 + ch * 8);
+          const float4 hb = *reinterpret_cast<const float4*>(hu_s + neuron0 + ch * 8 + 4);
+          uint32_t hw[4], lw[4];
+          bias_relu_split2(v[ch * 8 + 0], v[ch * 8 + 1], make_float2(ha.x, ha.y), hw[0], lw[0]);
+          bias_relu_split2(v[ch * 8 + 2], v[ch * 8 + 3], make_float2(ha.z, ha.w), hw[1], lw[1]);
+          bias_relu_split2(v[ch * 8 + 4], v[ch * 8 + 5], make_float2(hb.x, hb.y), hw[2], lw[2]);
+          bias_relu_split2(v[ch * 8 + 6], v[ch * 8 + 7], make_float2(hb.z, hb.w), hw[3], lw[3]);
+          const uint32_t off = sw128_chunk_off(row, col_half * 4 + ch);
+          *reinterpret_cast<uint4*>(dl + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          *reinterpret_cast<uint4*>(dl + TC_SLAB_BYTES + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        }
+        // the slab is complete in THIS CTA's slot once all epilogue threads are here; one thread publishes it locally
+        // and ships it to the peer's slot with DSMEM bulk copies (thread-level st.shared::cluster stores, 16 B per
+        // lane into 32 different rows, ran at ~9 B/clk; bulk copies reach ~17 B/clk with two in flight)
         fence_proxy_async();                                               // generic-proxy writes -> async proxy (UMMA, bulk copy)
-        if (col_half == 0) asm volatile("bar.sync 2, 128;" ::: "memory");
-        else               asm volatile("bar.sync 3, 128;" ::: "memory");
-        if ((ew & 3) == 0 && lane == 0) {
+        asm volatile("bar.sync 1, %0;" ::"n"(T2_EPI_THREADS) : "memory");
+        if (ew == 0 && lane == 0) {
           mbar_arrive(B(T8Bars::a_full + slot));
           const uint32_t rb = rbar0 + 8u * (uint32_t)(T8Bars::a_full + slot);
+          const uint32_t src = sA_u + slot * T2_STAGE, dst = rA_u + slot * T2_STAGE;
           mbar_expect_tx_remote(rb, T2_STAGE);
-          bulk_s2peer(dr, sA_u + slot * T2_STAGE, T2_STAGE, rb);
+          bulk_s2peer(dst, src, TC_SLAB_BYTES, rb);
+          bulk_s2peer(dst + TC_SLAB_BYTES, src + TC_SLAB_BYTES, TC_SLAB_BYTES, rb);
         }
-      }
-      tc_fence_before();
-      mbar_arrive(B(T8Bars::d1_empty));
+      };
+      slab(va, vb, 0);
+      slab(vb, va, 1);
+      slab(va, vb, 2);
+      slab(vb, va, 3);
     };
     // ---- epilogue 2 of tile j: partial score over this CTA's 256 layer-2 neurons
     auto epi2 = [&](int j, auto r_c, auto ch_c) -> float {

@@ -46,6 +46,10 @@ for tile in (10, 11):
     for ev in sorted(names, key=lambda e: t[tile][e]):
         if t[tile][ev]: print(f"{t[tile][ev]-base:9d}  {names[ev]}")
 b11 = t[11][0]
+if os.environ.get("NANN_TC_KERNEL", "3") == "8":
+    print("tile 11 units: (a_full ok, hi stage ok, lo stage ok, all issued) from tile start")
+    for u in range(10):
+        print(f"   unit {u}:", [int(x - b11) for x in t.reshape(-1)[60 * 48 + 4 * u:60 * 48 + 4 * u + 4]])
 print("tile 11 ring stages: producer saw slot empty:", [int(x - b11) for x in t[62][:40]])
 print("tile 11 ring stages: mma saw stage full:   ", [int(x - b11) for x in t[63][:40]])
 print("mma warp waits per tile: ring", [int(t[i][46]) for i in range(8, 12)], "a_full", [int(t[i][47]) for i in range(8, 12)])
