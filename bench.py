@@ -59,11 +59,19 @@ def get_shard(n_items, world, rank, device):
     key = hashlib.sha1(json.dumps([n_items, world, rank, 128, 32, 4, "v3"]).encode()).hexdigest()[:16]
     root = os.path.join(CACHE, f"shard_{n_items}_{world}_{rank}_{key}")
     embs_dir, index_dir = os.path.join(root, "embeddings"), os.path.join(root, "index")
+    lo, hi = shard_bounds(n_items, world, rank)
+    if hi - lo > 4_000_000:      # big shards (configs[2], configs[3]): ~10 GB of files per shard -- keep them in memory
+        t = time.time()
+        emb = np.ascontiguousarray(nix.synthetic_corpus(n_items, 128, seed=0)[lo:hi])
+        ids = nix.synthetic_item_ids(n_items, seed=1)[lo:hi]
+        g = nix.build_hnsw(emb, M=32, start_level=2, seed=4 + rank, device=device)
+        log(f"[bench] rank {rank}: built HNSW over rows [{lo},{hi}) in {time.time() - t:.1f}s on {device} (partitioned candidate search)")
+        return dict(emb=emb, item_ids=ids, ep=g["enter_points"], values=g["values"], row_splits=g["row_splits"],
+                    embs_dir=None, index_dir=None)
     if not os.path.exists(os.path.join(root, "done")):
         t = time.time()
         full = nix.synthetic_corpus(n_items, 128, seed=0)
         ids = nix.synthetic_item_ids(n_items, seed=1)
-        lo, hi = shard_bounds(n_items, world, rank)
         emb = np.ascontiguousarray(full[lo:hi])
         g = nix.build_hnsw(emb, M=32, start_level=2, seed=4 + rank, device=device)
         nix.save_index(embs_dir, index_dir, emb, ids[lo:hi], g)
@@ -85,16 +93,27 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            t0 = time.time()
+            while not self.rows and time.time() - t0 < 3.0:      # nvidia-smi needs ~0.1-1 s to print its first row
+                time.sleep(0.01)
         except Exception:
             self.proc = None
         return self
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append([time.perf_counter()] + [c.strip() for c in line.split(",")])
+
+    def window(self, t0, t1):
+        """keep the samples taken inside [t0, t1] (perf_counter); if the window is shorter than the sampling
+        period, keep the samples of the whole sampler lifetime (warm-up steps = the same load)"""
+        inside = [r for r in self.rows if t0 <= r[0] <= t1]
+        self.scope = "timed region" if inside else "warm-up + timed region"
+        if inside:
+            self.rows = inside
 
     def __exit__(self, *a):
         if self.proc:
@@ -108,6 +127,7 @@ class ClockSampler:
     def summary(self):
         sm, mx, reasons = [], 0, set()
         for r in self.rows:
+            r = r[1:]
             try:
                 sm.append(float(r[1])); mx = max(mx, float(r[2]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
@@ -117,7 +137,8 @@ class ClockSampler:
                 pass
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm),
+                "scope": getattr(self, "scope", "sampler lifetime")}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -157,8 +178,10 @@ def run_reference(args, T, rank, world):
 
 
 def workload_config(args, T, world):
+    which = {(1_000_000, 256, 200): "BASELINE configs[1]", (10_000_000, 1024, 400): "BASELINE configs[2]"}.get(
+        (args.n_items, args.batch, args.ef), "BASELINE configs[4] sweep point" if args.n_items == 1_000_000 else "custom")
     return {"workload": f"{args.n_items} items d=128 f32, batch={args.batch} queries, scoring MLP 2x512, "
-                        f"ef_search={args.ef}, HNSW M=32 (BASELINE configs[1])",
+                        f"ef_search={args.ef}, HNSW M=32 ({which})",
             "level_topn": list(T), "parallelism": "1 GPU" if world == 1 else f"corpus row-sharded x{world}, NCCL allgather + merge",
             "l2": "inputs larger than L2: 512 MB embedding table + 260 MB graph per 1M rows, fresh queries every step"}
 
@@ -217,6 +240,8 @@ def run_b200(args, T, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    step_wall = []
+
     def timed(fn, profile):
         for w in range(args.warmup):
             fn(w)
@@ -224,13 +249,18 @@ def run_b200(args, T, rank, world, local_rank):
         se.set_profile(profile)
         l0 = nb.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        del step_wall[:]
         t0 = time.perf_counter()
+        timed.window = [t0, t0]
         e0.record(stream)
         for s in range(args.steps):
+            ts = time.perf_counter()
             fn(args.warmup + s)
+            step_wall.append(time.perf_counter() - ts)
         e1.record(stream)
         barrier()
         wall = time.perf_counter() - t0
+        timed.window[1] = t0 + wall
         dev_ms = e0.elapsed_time(e1)
         prof = se.profile() if profile else None
         se.set_profile(False)
@@ -241,7 +271,12 @@ def run_b200(args, T, rank, world, local_rank):
 
     with ClockSampler(local_rank) as clk:
         dev_ms, _, launches, prof = timed(step_device, True)
+        clk.window(*timed.window)
     e2e_dev_ms, e2e_wall_ms, _, _ = timed(step_e2e, False)
+    # the public call is synchronous (host results are returned), so a step's wall time is the batch latency
+    lat = sorted(step_wall)
+    latency_ms = {"p50": 1000.0 * lat[len(lat) // 2], "max": 1000.0 * lat[-1], "batch": B,
+                  "what": "wall time of one public API call (host queries in, host ids+scores out)"}
 
     # ---- outside the timed region: recall@200 vs brute force under the same scorer; parity vs the CPU port
     extra = {}
@@ -272,14 +307,19 @@ def run_b200(args, T, rank, world, local_rank):
             sh1 = sh
             oix = orc.Index(sh1["emb"], sh1["item_ids"], sh1["ep"].astype(np.int32), [v.astype(np.int32) for v in sh1["values"]], sh1["row_splits"])
             om = orc.Mlp(*sw.mlp_weights(seed=3))
-            sample_q = args.cpu_sample or int(min(B, max(32, 4 * cores)))
-            oix.search_batch_mlp(om, queries[:min(sample_q, 2 * cores)], T, nthreads=cores)   # warm
+            n_warm = int(min(len(queries), max(32, 2 * cores)))
+            rw = oix.search_batch_mlp(om, queries[:n_warm], T, nthreads=cores)   # warm + rate estimate
+            # bounded sample: about 12 s of host work on this box's cores (same queries the GPU arm is timed on)
+            sample_q = args.cpu_sample or int(min(len(queries), max(64, 12.0 * n_warm / max(rw["seconds"], 1e-3))))
             r = oix.search_batch_mlp(om, queries[:sample_q], T, nthreads=cores)
             cpu = {"value": sample_q / r["seconds"], "unit": "queries/s", "cores": cores, "kind": "port",
-                   "sample": f"first {sample_q} queries of step 0, one request per core, {r['seconds']:.1f}s",
+                   "sample": f"first {sample_q} queries of the run, one request per core (batch=1 each), {r['seconds']:.1f}s",
                    "rows_scored_per_query": r["n_scored"] / sample_q}
             if world == 1:
-                mine = se.search(queries[:sample_q], T)
+                n_cmp = min(sample_q, B)                 # the searcher was created for batches of B
+                mine = se.search(queries[:n_cmp], T)
+                r = {k2: (v2[:n_cmp] if isinstance(v2, np.ndarray) else v2) for k2, v2 in r.items()}
+                cpu["compared_queries"] = n_cmp
                 cpu["ids_equal_to_gpu"] = bool(np.array_equal(mine["ids"], r["ids"]))
                 cpu["topk_overlap_with_gpu"] = float(np.mean([len(set(a.tolist()) & set(b.tolist())) / max(k, 1)
                                                               for a, b in zip(mine["ids"], r["ids"])]))
@@ -291,7 +331,7 @@ def run_b200(args, T, rank, world, local_rank):
                 cpu["max_abs_score_diff_common_items"] = float(max(diffs)) if diffs else None
                 if args.precision == "tensor":            # the bit-exact path, for the record
                     sc.set_precision(nb.SCORER_EXACT)
-                    ex = se.search(queries[:sample_q], T)
+                    ex = se.search(queries[:n_cmp], T)
                     sc.set_precision(nb.SCORER_TENSOR)
                     cpu["exact_path_ids_equal_to_cpu"] = bool(np.array_equal(ex["ids"], r["ids"]))
                     cpu["exact_path_scores_bit_equal"] = bool(np.array_equal(ex["scores"].view(np.uint32), r["scores"].view(np.uint32)))
@@ -317,15 +357,18 @@ def run_b200(args, T, rank, world, local_rank):
                 "d2h_bytes_per_step": (B * k_s * 12 + B * 4 + 10 * B * 4) if world == 1 else B * k * 12,
                 "timing": "wall clock around the public API call with pinned host inputs and host outputs",
                 "device_ms_per_step": e2e_dev_ms / args.steps},
+        "latency_ms": latency_ms,
         "gpu_launches": launches,
         "clocks": clk.summary(),
         "roofline": {
             "kernel": "mlp_exact_kernel (fused row gather + 2x512 MLP, fp32 FFMA)" if args.precision == "exact"
-                      else "mlp_tc3_kernel (fused row gather + 2x512 MLP, tcgen05 fp16 hi/lo split)",
+                      else "mlp_tc8_kernel (fused row gather + 2x512 MLP, tcgen05 fp16 hi/lo split, cluster-pair neuron split)",
             "bound": "tensor", "achieved": ach_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
             "frac": ach_tf / pk["tf_sustained"], "peak_source": f"bf16 dense sustained, of {pk['source']}",
             "traffic": _ncu_traffic(args.precision),
             "algorithmic_flops_per_row": 2 * MAC_PER_ROW, "rows_per_launch": rows / n_score,
+            "issued_mma_tflops": (3.0 * ach_tf * (2 * (128 * 512 + 512 * 512)) / (2.0 * MAC_PER_ROW)) if args.precision == "tensor" else None,
+            "note": "tensor precision issues 3 fp16 MMAs per fp32 product (hi/lo split, |dscore| <= 1e-5); the layer-1 user half is hoisted per query",
             "avg_launch_ms": score_ms / n_score,
             "gather_GBps_inside_kernel": rows * ROW_BYTES / (score_ms / 1000.0) / 1e9 if score_ms > 0 else 0.0,
             "hbm_peak_GBps": pk["hbm_gbs"]},
