@@ -8,7 +8,7 @@ visited-filter rounds, 6 top-k) on synthetic data.  Default workload = BASELINE 
 
   python bench.py --gpus 1 --steps 10 --warmup 3            # this repo's CUDA path
   python bench.py --impl reference ...                       # the reference algorithm on the host cores
-  torchrun --nproc-per-node N bench.py --gpus N ...          # corpus row-sharded over N GPUs (strong scaling)
+  torchrun --nproc-per-node N bench.py --gpus N ...          # N shards of --n-items rows, global batch N x --batch (weak scaling)
 
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
 """
@@ -53,9 +53,36 @@ def peaks():
 from nann_b200.distributed import shard_bounds, shard_level_topn as shard_topn  # noqa: E402
 
 
-def get_shard(n_items, world, rank, device):
-    """-> dict(emb, item_ids (GLOBAL ids), ep, values, row_splits) for this rank's row range."""
+def corpus_block(n_rows, block):
+    """rows and GLOBAL item ids of block `block` of the sharded corpus (N>1): the corpus is DEFINED as the
+    concatenation of per-rank blocks (seed 100+block), so no rank ever materialises more than its own block
+    (+ block 0, which the queries are drawn from)."""
     from nann_b200 import index as nix
+    emb = nix.synthetic_corpus(n_rows, 128, seed=100 + block)
+    ids = np.int64(block) * n_rows + nix.synthetic_item_ids(n_rows, seed=200 + block)
+    return emb, ids
+
+
+def get_shard(n_items, world, rank, device):
+    """-> dict(emb, item_ids (GLOBAL ids), ep, values, row_splits) for this rank's rows.
+    world == 1: the whole n_items corpus (seed 0).  world > 1 (weak scaling): block `rank` of n_items rows."""
+    from nann_b200 import index as nix
+    if world > 1:
+        key = hashlib.sha1(json.dumps([n_items, "block", rank, 128, 32, 4, "w1"]).encode()).hexdigest()[:16]
+        root = os.path.join(CACHE, f"block_{n_items}_{rank}_{key}")
+        embs_dir, index_dir = os.path.join(root, "embeddings"), os.path.join(root, "index")
+        big = n_items > 4_000_000
+        if big or not os.path.exists(os.path.join(root, "done")):
+            t = time.time()
+            emb, ids = corpus_block(n_items, rank)
+            g = nix.build_hnsw(emb, M=32, start_level=2, seed=4 + rank, device=device)
+            log(f"[bench] rank {rank}: built HNSW over block {rank} ({n_items} rows) in {time.time() - t:.1f}s on {device}")
+            if big:
+                return dict(emb=emb, item_ids=ids, ep=g["enter_points"], values=g["values"], row_splits=g["row_splits"])
+            nix.save_index(embs_dir, index_dir, emb, ids, g)
+            open(os.path.join(root, "done"), "w").write("ok")
+        emb, item_ids, g = nix.load_index_arrays(embs_dir, index_dir)
+        return dict(emb=emb, item_ids=item_ids, ep=g["enter_points"], values=g["values"], row_splits=g["row_splits"])
     key = hashlib.sha1(json.dumps([n_items, world, rank, 128, 32, 4, "v3"]).encode()).hexdigest()[:16]
     root = os.path.join(CACHE, f"shard_{n_items}_{world}_{rank}_{key}")
     embs_dir, index_dir = os.path.join(root, "embeddings"), os.path.join(root, "index")
@@ -169,7 +196,7 @@ def run_reference(args, T, rank, world):
     sample = f"{sample_q} queries/step (of the {args.batch}-query batch), {args.steps} steps, one request per core"
     return {"impl": "reference", "metric": "queries/sec at fixed recall@200", "value": qps, "unit": "queries/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1000.0 * secs / args.steps, "higher_is_better": True, "scaling": "strong",
+            "ms_per_step": 1000.0 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, T, 1),
             "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample,
@@ -180,9 +207,16 @@ def run_reference(args, T, rank, world):
 def workload_config(args, T, world):
     which = {(1_000_000, 256, 200): "BASELINE configs[1]", (10_000_000, 1024, 400): "BASELINE configs[2]"}.get(
         (args.n_items, args.batch, args.ef), "BASELINE configs[4] sweep point" if args.n_items == 1_000_000 else "custom")
+    if world > 1:
+        return {"workload": f"{world} x {args.n_items} items d=128 f32 (one {args.n_items}-row shard + its own HNSW per GPU), global batch="
+                            f"{args.batch * world} queries, scoring MLP 2x512, ef_search={args.ef} split over the shards, HNSW M=32 "
+                            f"(BASELINE configs[3] shape at {args.n_items} rows per GPU)",
+                "level_topn": list(T), "parallelism": f"corpus row-sharded x{world}: every query visits every shard, one NCCL allgather of "
+                                                      f"per-shard top-k + merge kernel; weak scaling (rows and queries per step grow with N)",
+                "l2": "inputs larger than L2: 512 MB embedding table + 260 MB graph per 1M rows, fresh queries every step"}
     return {"workload": f"{args.n_items} items d=128 f32, batch={args.batch} queries, scoring MLP 2x512, "
                         f"ef_search={args.ef}, HNSW M=32 ({which})",
-            "level_topn": list(T), "parallelism": "1 GPU" if world == 1 else f"corpus row-sharded x{world}, NCCL allgather + merge",
+            "level_topn": list(T), "parallelism": "1 GPU",
             "l2": "inputs larger than L2: 512 MB embedding table + 260 MB graph per 1M rows, fresh queries every step"}
 
 
@@ -199,12 +233,14 @@ def run_b200(args, T, rank, world, local_rank):
     sc = nb.Scorer.mlp(*sw.mlp_weights(seed=3), device=local_rank)
     if args.precision == "tensor":
         sc.set_precision(nb.SCORER_TENSOR)
-    se = nb.Searcher(ix, sc, args.batch, Ts)
-    B, k_s, k = args.batch, Ts[5], T[5]
+    B = args.batch * world          # N > 1: the global batch grows with N and every shard sees all of it
+    se = nb.Searcher(ix, sc, B, Ts)
+    k_s, k = Ts[5], T[5]
     n_steps = args.warmup + args.steps
-    # queries are drawn from the FULL corpus so that every rank sees the same ones
-    full = nix.synthetic_corpus(args.n_items, 128, seed=0) if world > 1 else sh["emb"]
+    # every rank draws the same queries (from block 0 of the sharded corpus)
+    full = sh["emb"] if (world == 1 or rank == 0) else corpus_block(args.n_items, 0)[0]
     queries = nix.synthetic_queries(full, B * n_steps, seed=2)
+    del full
     q_dev = torch.from_numpy(queries).to(dev)
     q_pin = torch.from_numpy(queries).pin_memory()
     ids_d = torch.empty((B, k_s), dtype=torch.int64, device=dev)
@@ -212,14 +248,28 @@ def run_b200(args, T, rank, world, local_rank):
     if world > 1:
         g_ids = torch.empty((world * B, k_s), dtype=torch.int64, device=dev)
         g_sc = torch.empty((world * B, k_s), dtype=torch.float32, device=dev)
+        m_ids = torch.empty((B, k), dtype=torch.int64, device=dev)
+        m_sc = torch.empty((B, k), dtype=torch.float32, device=dev)
     stream = torch.cuda.current_stream()
 
+    dbg = {"search_ms": 0.0, "exchange_ms": 0.0, "merge_ms": 0.0} if os.environ.get("NANN_BENCH_DEBUG") else None
+
     def step_device(i):
+        if dbg is not None and world > 1:      # per-phase wall clock with synchronisation (debug only: serialises the step)
+            t0 = time.perf_counter()
+            se.search_device(q_dev[i * B:(i + 1) * B], Ts, ids_d, sc_d, stream=stream); torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            dist.all_gather_into_tensor(g_sc, sc_d); dist.all_gather_into_tensor(g_ids, ids_d); torch.cuda.synchronize()
+            t2 = time.perf_counter()
+            r = nb.merge_topk(g_sc.view(world, B, k_s), g_ids.view(world, B, k_s), k)
+            t3 = time.perf_counter()
+            dbg["search_ms"] += 1e3 * (t1 - t0); dbg["exchange_ms"] += 1e3 * (t2 - t1); dbg["merge_ms"] += 1e3 * (t3 - t2)
+            return r
         status, _ = se.search_device(q_dev[i * B:(i + 1) * B], Ts, ids_d, sc_d, stream=stream)
-        if world > 1:
+        if world > 1:     # inputs and the merged result stay in HBM
             dist.all_gather_into_tensor(g_sc, sc_d)
             dist.all_gather_into_tensor(g_ids, ids_d)
-            return nb.merge_topk(g_sc.view(world, B, k_s), g_ids.view(world, B, k_s), k)
+            return nb.merge_topk(g_sc.view(world, B, k_s), g_ids.view(world, B, k_s), k, out_scores=m_sc, out_ids=m_ids)
         return status
 
     q_step = torch.empty((B, 128), dtype=torch.float32, device=dev)
@@ -284,18 +334,26 @@ def run_b200(args, T, rank, world, local_rank):
         n_eval = min(args.eval_queries, B)
         if n_eval <= 0:
             raise RuntimeError("recall evaluation disabled (--eval-queries 0)")
-        res = step_e2e(0)
+        if world > 1:
+            n_eval = min(n_eval, 4)
+        res = step_e2e(0)                                # all ranks take part (collective inside)
         got_ids = (res[1] if world > 1 else res["ids"])[:n_eval]
-        emb_t = torch.from_numpy(full).to(dev)          # whole corpus (== this shard when world == 1)
-        all_ids = nix.synthetic_item_ids(args.n_items, seed=1) if world > 1 else sh["item_ids"]
-        hits = 0
-        for q in range(n_eval):
-            s_all = nb.blaze_xla_op(sc, queries[q], emb_t)                 # scores of the WHOLE corpus
-            top = np.argpartition(-s_all, k)[:k]
-            hits += len(set(all_ids[top].tolist()) & set(got_ids[q].tolist()))
-        del emb_t
-        extra["recall_at_k_vs_bruteforce"] = hits / (n_eval * k)
-        extra["recall_queries"] = n_eval
+        if rank == 0:
+            best_s = [np.empty(0, np.float32) for _ in range(n_eval)]
+            best_i = [np.empty(0, np.int64) for _ in range(n_eval)]
+            for b in range(world):                       # brute force over the WHOLE corpus, one block at a time
+                emb_b, ids_b = (sh["emb"], sh["item_ids"]) if b == rank else corpus_block(args.n_items, b)
+                emb_t = torch.from_numpy(emb_b).to(dev)
+                for q in range(n_eval):
+                    s_all = nb.blaze_xla_op(sc, queries[q], emb_t)
+                    top = np.argpartition(-s_all, k)[:k]
+                    cs, ci = np.concatenate([best_s[q], s_all[top]]), np.concatenate([best_i[q], ids_b[top]])
+                    keep = np.argsort(-cs, kind="stable")[:k]
+                    best_s[q], best_i[q] = cs[keep], ci[keep]
+                del emb_t
+            hits = sum(len(set(best_i[q].tolist()) & set(got_ids[q].tolist())) for q in range(n_eval))
+            extra["recall_at_k_vs_bruteforce"] = hits / (n_eval * k)
+            extra["recall_queries"] = n_eval
     except Exception as e:  # never lose the bench line over the side measurements
         extra["recall_error"] = repr(e)[:200]
 
@@ -350,7 +408,7 @@ def run_b200(args, T, rank, world, local_rank):
     out = {
         "metric": "queries/sec at fixed recall@200", "value": qps, "unit": "queries/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": dict(workload_config(args, T, world), shard_level_topn=Ts, scorer_precision=args.precision),
         "e2e": {"value": B * args.steps / (e2e_wall_ms / 1000.0), "unit": "queries/s",
                 "h2d_bytes_per_step": B * 128 * 4,
@@ -378,6 +436,8 @@ def run_b200(args, T, rank, world, local_rank):
         "cpu_baseline": cpu,
     }
     out.update(extra)
+    if dbg is not None:
+        out["debug"] = {k2: v / (args.steps + args.warmup) for k2, v in dbg.items()}
     return out
 
 
@@ -410,10 +470,20 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
+    # Only the JSON line may reach stdout: libraries (NCCL's version banner) print there too, so fd 1 is pointed at
+    # stderr for the duration of the run and the line is written to the saved descriptor.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
     if args.impl == "reference":
         out = run_reference(args, T, rank, world)
         if out is not None:
-            print(json.dumps(out), flush=True)
+            emit(out)
         return
 
     import torch
@@ -426,7 +496,7 @@ def main():
     try:
         out = run_b200(args, T, rank, world, local_rank)
         if out is not None:
-            print(json.dumps(out), flush=True)
+            emit(out)
     finally:
         if world > 1:
             import torch.distributed as dist

@@ -356,8 +356,10 @@ def score_ids(scorer, user, table, ids, stream=None):
     return out
 
 
-def merge_topk(scores, ids, k_out, stream=None):
-    """Per-shard results [G][B][k_in] (allgather layout) -> global top k_out per query."""
+def merge_topk(scores, ids, k_out, stream=None, out_scores=None, out_ids=None):
+    """Per-shard results [G][B][k_in] (allgather layout) -> global top k_out per query.
+    With `out_scores` f32[B,k_out] / `out_ids` i64[B,k_out] CUDA tensors the result stays on the device
+    (returned as given); otherwise host arrays are returned."""
     if _is_torch(scores):
         s, i = scores.contiguous().float(), ids.contiguous()
         G, B, k_in = s.shape
@@ -366,6 +368,11 @@ def merge_topk(scores, ids, k_out, stream=None):
         s, i = np.ascontiguousarray(scores, np.float32), np.ascontiguousarray(ids, np.int64)
         G, B, k_in = s.shape
         sp, ip = C.c_void_p(s.ctypes.data), C.c_void_p(i.ctypes.data)
+    if out_scores is not None and out_ids is not None:
+        assert tuple(out_scores.shape) == (B, k_out) and tuple(out_ids.shape) == (B, k_out)
+        check(_lib.lib().nann_merge_topk(sp, ip, G, B, k_in, int(k_out), C.c_void_p(out_scores.data_ptr()),
+                                         C.c_void_p(out_ids.data_ptr()), _stream_ptr(stream)))
+        return out_scores, out_ids
     osc = np.empty((B, k_out), np.float32)
     oid = np.empty((B, k_out), np.int64)
     check(_lib.lib().nann_merge_topk(sp, ip, G, B, k_in, int(k_out), C.c_void_p(osc.ctypes.data),
