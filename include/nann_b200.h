@@ -263,6 +263,28 @@ nann_status nann_searcher_get_trace(nann_searcher_t* s, int q, int round, int32_
 nann_status nann_searcher_set_profile(nann_searcher_t* s, int enable);
 nann_status nann_searcher_get_profile(nann_searcher_t* s, double stage_ms[4], int64_t stage_launches[4],
                                       int64_t* rows_scored, int64_t* calls);
+
+/* ---- the `main.py --job-type test` traversal ----------------------------------
+ * Replaces Model.retrieval / Model.search_level (NANN_impls/nann/model/model.py:299-362), the graph
+ * `main.py test` runs once per user (main.py:150-190), for a batch of users: start level = 2, every
+ * enter point scored once, then per level the UNIQUE unvisited neighbours of the frontier in ascending
+ * id order (tf.unique + tf.sets.set_difference, :319-322), merged into the running result with a
+ * clamped k (:268, :329-331), next frontier = new nodes whose score reaches the worst kept score
+ * (:333-334).  num_scoring_per_level / top_k_per_level are indexed by LEVEL 0..2 like the reference's
+ * flags (nann/config.py:52-55, defaults [3,1,1] / [400,200,100]); topk_eval = --topk-eval.
+ * out_item_ids/out_scores/out_nodes [B][topk_eval] (-1 / 0 padded), out_n[B] = valid results per
+ * query, out_status[B]: InvalidArgument where the reference's graph fails (a round with exactly one
+ * new candidate: tf.squeeze yields a scalar that cannot be concatenated), ResourceExhausted when
+ * a round produced more candidates than the workspace holds.  Host or device pointers. */
+typedef struct nann_eval_searcher nann_eval_searcher_t;
+nann_status nann_eval_searcher_create(const nann_index_t* ix, nann_scorer_t* scorer, int max_batch,
+                                      const int32_t max_top_k_per_level[3], int max_topk_eval,
+                                      nann_eval_searcher_t** out);
+void nann_eval_searcher_destroy(nann_eval_searcher_t* s);
+nann_status nann_search_eval_batch(nann_eval_searcher_t* s, const float* users, int B,
+                                   const int32_t num_scoring_per_level[3], const int32_t top_k_per_level[3],
+                                   int topk_eval, int64_t* out_item_ids, float* out_scores, int32_t* out_nodes,
+                                   int32_t* out_n, int32_t* out_status, int64_t* n_scored_total, void* stream);
 /* node ids (rows of the table) of the last call's final top-k, [B][k], before the item_ids gather */
 nann_status nann_searcher_get_nodes(nann_searcher_t* s, int32_t* out_nodes, int64_t cap);
 

@@ -97,6 +97,10 @@ def lib():
     L.nann_searcher_set_profile.argtypes = [vp, i32]
     L.nann_searcher_get_profile.argtypes = [vp, vp, vp, vp, vp]
     L.nann_merge_topk.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp]
+    L.nann_eval_searcher_create.argtypes = [vp, vp, i32, vp, i32, vp]
+    L.nann_eval_searcher_destroy.restype = None
+    L.nann_eval_searcher_destroy.argtypes = [vp]
+    L.nann_search_eval_batch.argtypes = [vp, vp, i32, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp]
     _lib = L
     return L
 

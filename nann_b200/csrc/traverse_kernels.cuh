@@ -289,17 +289,20 @@ struct TopkArgs {
   // ragged form (BatchTopKOnRT): row r = b_sc[b_row_off[r] .. b_row_off[r+1]), k = min(len, k_ptr[r] or k),
   // outputs at out_row_off[r]; group-local positions as int64; ascending flips the value order
   const int64_t* b_row_off; const int64_t* k_ptr; const int64_t* out_row_off; int64_t* out_pos64; int ascending;
+  // eval traversal (model.py:255-271): list a has a per-row length, k is clamped to the row length, the
+  // number of results per row is reported
+  const int32_t* a_n_ptr; int clamp; int32_t* out_n;
 };
 
 constexpr int TOPK_THREADS = 512;
 constexpr int TOPK_MAX_K = 4096;
 
-__device__ __forceinline__ float topk_score_at(const TopkArgs& a, int64_t row, int i) {
+__device__ __forceinline__ float topk_score_at(const TopkArgs& a, int64_t row, int i, int a_n) {
   if (a.b_row_off) return a.b_sc[a.b_row_off[row] + i];
-  return i < a.a_n ? a.a_sc[row * a.a_stride + i] : a.b_sc[row * a.b_sc_stride + (i - a.a_n)];
+  return i < a_n ? a.a_sc[row * a.a_stride + i] : a.b_sc[row * a.b_sc_stride + (i - a_n)];
 }
-__device__ __forceinline__ uint32_t topk_key_at(const TopkArgs& a, int64_t row, int i) {
-  const uint32_t key = order_key(topk_score_at(a, row, i));
+__device__ __forceinline__ uint32_t topk_key_at(const TopkArgs& a, int64_t row, int i, int a_n) {
+  const uint32_t key = order_key(topk_score_at(a, row, i, a_n));
   return a.ascending ? ~key : key;
 }
 
@@ -314,8 +317,10 @@ topk_kernel(TopkArgs a) {
   if (a.status && a.status[row] != 0) return;
   const int b_n = a.b_row_off ? (int)(a.b_row_off[row + 1] - a.b_row_off[row])
                               : (a.b_n_ptr ? a.b_n_ptr[row] : a.b_n_fixed);
-  const int n = a.a_n + b_n;
+  const int a_n = a.a_n_ptr ? a.a_n_ptr[row] : a.a_n;
+  const int n = a_n + b_n;
   int k = a.k;
+  if (a.clamp) k = k < n ? k : n;
   if (a.b_row_off) {  // BatchTopKOnRT: k[g] (or scalar k) clamped to the group length (:117-121)
     const long long kk = a.k_ptr ? a.k_ptr[row] : (long long)a.k;
     k = (int)(kk < 0 ? 0 : (kk < n ? kk : n));
@@ -324,6 +329,7 @@ topk_kernel(TopkArgs a) {
     if (tid == 0 && a.status) a.status[row] = NANN_INVALID_ARGUMENT;
     return;
   }
+  if (a.out_n && tid == 0) a.out_n[row] = k;
   if (k == 0) return;
 
   // --- radix select (MSD, 8 bits per pass): key of the k-th best -> s_prefix
@@ -334,7 +340,7 @@ topk_kernel(TopkArgs a) {
     __syncthreads();
     const int shift = pass * 8;
     for (int i = tid; i < n; i += TOPK_THREADS) {
-      const uint32_t key = topk_key_at(a, row, i);
+      const uint32_t key = topk_key_at(a, row, i, a_n);
       if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255], 1);
     }
     __syncthreads();
@@ -378,7 +384,7 @@ topk_kernel(TopkArgs a) {
   if (tid == 0) { s_cnt = 0; s_eq_taken = 0; }
   __syncthreads();
   for (int i = tid; i < n; i += TOPK_THREADS) {
-    const uint32_t key = topk_key_at(a, row, i);
+    const uint32_t key = topk_key_at(a, row, i, a_n);
     if (key > thr) {
       const int slot = atomicAdd(&s_cnt, 1);
       sel[slot] = ((unsigned long long)(~key) << 32) | (uint32_t)i;
@@ -390,7 +396,7 @@ topk_kernel(TopkArgs a) {
     for (int base = 0; base < n; base += TOPK_THREADS) {
       if (s_eq_taken >= eq_take) break;  // uniform: read after the barrier below / initial sync
       const int i = base + tid;
-      const bool eq = (i < n) && (topk_key_at(a, row, i) == thr);
+      const bool eq = (i < n) && (topk_key_at(a, row, i, a_n) == thr);
       const unsigned bm = __ballot_sync(FULL, eq);
       if (lane == 0) s_warp_cnt[wid] = __popc(bm);
       __syncthreads();
@@ -427,14 +433,14 @@ topk_kernel(TopkArgs a) {
   // --- emit
   for (int r = tid; r < k; r += TOPK_THREADS) {
     const int pos = (int)(uint32_t)(sel[r] & 0xffffffffull);
-    const float sc = topk_score_at(a, row, pos);
+    const float sc = topk_score_at(a, row, pos, a_n);
     const int64_t o = (a.out_row_off ? a.out_row_off[row] : row * a.out_stride + a.out_offset) + r;
     if (a.out_sc) a.out_sc[o] = sc;
     if (a.out_pos) a.out_pos[o] = pos;
     if (a.out_pos64) a.out_pos64[o] = pos;
     int32_t id = pos;
     if (a.a_ids || a.b_ids)
-      id = pos < a.a_n ? a.a_ids[row * a.a_stride + pos] : a.b_ids[row * a.b_ids_stride + (pos - a.a_n)];
+      id = pos < a_n ? a.a_ids[row * a.a_stride + pos] : a.b_ids[row * a.b_ids_stride + (pos - a_n)];
     if (a.out_ids) a.out_ids[o] = id;
     if (a.out_item_ids) a.out_item_ids[row * a.out_item_stride + r] = a.item_ids[id];
   }

@@ -83,6 +83,49 @@ class Index:
             pass
 
 
+class EvalSearcher:
+    """The `main.py --job-type test` traversal (NANN_impls/nann/model/model.py:299-362) for batches of users.
+    Arguments keep the reference's flag names (nann/config.py:52-57), indexed by level 0..2."""
+
+    def __init__(self, index, scorer, max_batch, max_top_k_per_level=(400, 200, 100), max_topk_eval=200):
+        self.index, self.scorer = index, scorer
+        self.max_batch = int(max_batch)
+        K = (C.c_int32 * 3)(*[int(k) for k in max_top_k_per_level])
+        h = C.c_void_p()
+        check(_lib.lib().nann_eval_searcher_create(index._h, scorer._h, self.max_batch, K, int(max_topk_eval), C.byref(h)))
+        self._h = h
+
+    def search(self, users, num_scoring_per_level=(3, 1, 1), top_k_per_level=(400, 200, 100), topk_eval=200, stream=None):
+        """users: [B, user_floats] numpy or CUDA tensor.
+        Returns dict(ids i64[B,k] (-1 padded), scores f32[B,k], nodes i32[B,k], n i32[B], status i32[B], n_scored)."""
+        uf = self.scorer.user_floats
+        if ops._is_torch(users):
+            u = users.contiguous().float().reshape(-1, uf)
+            B, uptr = u.shape[0], C.c_void_p(u.data_ptr())
+        else:
+            u = np.ascontiguousarray(users, np.float32).reshape(-1, uf)
+            B, uptr = u.shape[0], C.c_void_p(u.ctypes.data)
+        k = int(topk_eval)
+        ns = (C.c_int32 * 3)(*[int(x) for x in num_scoring_per_level])
+        tk = (C.c_int32 * 3)(*[int(x) for x in top_k_per_level])
+        ids, sc, nodes = np.empty((B, k), np.int64), np.empty((B, k), np.float32), np.empty((B, k), np.int32)
+        n, status = np.empty(B, np.int32), np.empty(B, np.int32)
+        tot = C.c_int64(0)
+        check(_lib.lib().nann_search_eval_batch(self._h, uptr, B, ns, tk, k, C.c_void_p(ids.ctypes.data),
+                                                C.c_void_p(sc.ctypes.data), C.c_void_p(nodes.ctypes.data),
+                                                C.c_void_p(n.ctypes.data), C.c_void_p(status.ctypes.data), C.byref(tot),
+                                                ops._stream_ptr(stream)))
+        return dict(ids=ids, scores=sc, nodes=nodes, n=n, status=status, n_scored=tot.value)
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                _lib.lib().nann_eval_searcher_destroy(h)
+            except Exception:
+                pass
+
+
 class Searcher:
     """Workspace + launch sequence for batches of queries against one index and one scorer."""
 

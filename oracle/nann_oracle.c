@@ -663,6 +663,119 @@ done:
   return st;
 }
 
+/* ------------------------------------------------------------------------------------------
+ * `main.py --job-type test` traversal -- NANN_impls/nann/model/model.py:299-362.
+ * Differs from exec.pb: candidates of a round are the UNIQUE unvisited neighbours in ascending id
+ * order (tf.unique + tf.sets.set_difference, :319-322), the running result is merged with clamped k
+ * (:268,:329-331), the next frontier is the new nodes that made the cut (:333-334), and the visited
+ * set of a level starts as the level's entry results (:312).
+ * ---------------------------------------------------------------------------------------- */
+int orc_search_eval(const orc_index_t* ix, orc_score_fn score, void* score_ctx,
+                    const int32_t* num_scoring_per_level, const int32_t* top_k_per_level, int topk_eval,
+                    int64_t* out_ids, float* out_scores, int32_t* out_nodes, int32_t* out_n,
+                    int64_t* n_scored_total) {
+  int st = ORC_OK;
+  const int start_level = 2;                               /* levels 1 and 0 carry neighbour lists */
+  const int64_t W = (ix->n_items + 31) / 32;
+  uint32_t* visited = (uint32_t*)malloc((size_t)(W > 0 ? W : 1) * sizeof(uint32_t));
+  uint32_t* cand = (uint32_t*)calloc((size_t)(W > 0 ? W : 1), sizeof(uint32_t));
+  vec_t R = {0}, Nx = {0}, cat = {0}, C = {0};
+  int64_t scored = 0;
+  int round = 0;
+  if (out_n) *out_n = 0;
+  if (num_scoring_per_level[start_level] != 1) { st = ORC_INVALID_ARGUMENT; goto done; }   /* assert :347 */
+
+#define TOPK_CLAMPED(src, kk, dst)                                                              \
+  do {                                                                                          \
+    const int kc = (int)((src).n < (int64_t)(kk) ? (src).n : (int64_t)(kk));  /* reduce_min :268 */ \
+    vec_reserve(&(dst), kc + 1);                                                                \
+    int32_t* idx_tmp_ = (int32_t*)malloc((size_t)(kc > 0 ? kc : 1) * sizeof(int32_t));          \
+    st = kc > 0 ? topk_ids((src).ids, (src).sc, (src).n, kc, (dst).ids, (dst).sc, idx_tmp_) : ORC_OK; \
+    free(idx_tmp_);                                                                             \
+    (dst).n = kc;                                                                               \
+    if (st != ORC_OK) goto done;                                                                \
+  } while (0)
+
+  /* start level (:350-354): every enter point is scored */
+  vec_reserve(&Nx, ix->n_ep + 1);
+  memcpy(Nx.ids, ix->ep, (size_t)ix->n_ep * sizeof(int32_t));
+  Nx.n = ix->n_ep;
+  if (Nx.n == 1) { st = ORC_INVALID_ARGUMENT; goto done; }   /* tf.squeeze -> scalar, top_k needs rank >= 1 */
+  if (Nx.n > 0) score(score_ctx, round, Nx.ids, Nx.n, Nx.sc);
+  scored += Nx.n; ++round;
+  TOPK_CLAMPED(Nx, top_k_per_level[start_level], R);
+
+  for (int level = start_level - 1; level >= 0; --level) {   /* :356-357 */
+    memset(visited, 0, (size_t)W * sizeof(uint32_t));         /* visited_idx = idx_ep :312 */
+    for (int64_t i = 0; i < R.n; ++i) visited[R.ids[i] >> 5] |= 1u << (R.ids[i] & 31);
+    vec_reserve(&C, R.n + 1);
+    memcpy(C.ids, R.ids, (size_t)R.n * 4);
+    C.n = R.n;
+    for (int it = 0; it < num_scoring_per_level[level]; ++it) {   /* :317 */
+      /* neighbours of the frontier, unique, minus visited, ascending (:319-322) */
+      int64_t lo_w = W, hi_w = -1;
+      for (int64_t i = 0; i < C.n; ++i) {
+        const int64_t b = ix->nbr_row_splits[level][C.ids[i]], e = ix->nbr_row_splits[level][C.ids[i] + 1];
+        for (int64_t j = b; j < e; ++j) {
+          const int32_t v = ix->nbr_values[level][j];
+          const int64_t w = v >> 5;
+          if (!((visited[w] >> (v & 31)) & 1u)) {
+            cand[w] |= 1u << (v & 31);
+            if (w < lo_w) lo_w = w;
+            if (w > hi_w) hi_w = w;
+          }
+        }
+      }
+      Nx.n = 0;
+      for (int64_t w = lo_w; w <= hi_w; ++w) {
+        uint32_t bits = cand[w];
+        if (!bits) continue;
+        visited[w] |= bits;                                    /* set_union :324 */
+        cand[w] = 0;
+        while (bits) {
+          const int b = __builtin_ctz(bits);
+          bits &= bits - 1;
+          vec_reserve(&Nx, Nx.n + 64);
+          Nx.ids[Nx.n++] = (int32_t)(w * 32 + b);
+        }
+      }
+      if (Nx.n == 1) { st = ORC_INVALID_ARGUMENT; goto done; } /* scalar scores cannot be concatenated :329 */
+      vec_reserve(&Nx, Nx.n + 1);
+      if (Nx.n > 0) score(score_ctx, round, Nx.ids, Nx.n, Nx.sc);   /* :326 */
+      scored += Nx.n; ++round;
+      /* merged running result, clamped k (:329-331) */
+      vec_reserve(&cat, R.n + Nx.n + 1);
+      memcpy(cat.ids, R.ids, (size_t)R.n * 4); memcpy(cat.ids + R.n, Nx.ids, (size_t)Nx.n * 4);
+      memcpy(cat.sc, R.sc, (size_t)R.n * 4);   memcpy(cat.sc + R.n, Nx.sc, (size_t)Nx.n * 4);
+      cat.n = R.n + Nx.n;
+      TOPK_CLAMPED(cat, top_k_per_level[level], R);
+      /* frontier = new nodes whose score reaches the worst kept score (:333-334) */
+      C.n = 0;
+      vec_reserve(&C, Nx.n + 1);
+      if (R.n > 0) {
+        const float cut = R.sc[R.n - 1];
+        for (int64_t i = 0; i < Nx.n; ++i)
+          if (Nx.sc[i] >= cut) C.ids[C.n++] = Nx.ids[i];
+      }
+    }
+  }
+  {
+    const int64_t n_out = R.n < topk_eval ? R.n : topk_eval;   /* results[:topk_eval] :359 */
+    for (int64_t i = 0; i < n_out; ++i) {
+      if (out_nodes) out_nodes[i] = R.ids[i];
+      if (out_scores) out_scores[i] = R.sc[i];
+      if (out_ids) out_ids[i] = ix->item_ids[R.ids[i]];
+    }
+    if (out_n) *out_n = (int32_t)n_out;
+  }
+done:
+#undef TOPK_CLAMPED
+  if (n_scored_total) *n_scored_total = scored;
+  vec_free(&R); vec_free(&Nx); vec_free(&cat); vec_free(&C);
+  free(visited); free(cand);
+  return st;
+}
+
 /* ---- batch of queries with the mlp scorer, request-parallel ------------------------------ */
 typedef struct {
   const orc_index_t* ix; const orc_mlp_t* m; float* hu; float* scratch;

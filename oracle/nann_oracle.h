@@ -144,6 +144,17 @@ int orc_search(const orc_index_t* ix, orc_score_fn score, void* score_ctx,
                orc_search_stats_t* stats,
                int32_t** trace_ids, float** trace_scores, int64_t* trace_n, int64_t trace_cap);
 
+/* `main.py --job-type test` traversal, one query: NANN_impls/nann/model/model.py:299-362.
+ * num_scoring_per_level[3] / top_k_per_level[3] are indexed by LEVEL (0..2) like the reference's flags
+ * (config.py:52-55: defaults [3,1,1] / [400,200,100]); start level 2 scores every enter point once.
+ * round numbers passed to `score` count scoring calls from 0.  out_* need topk_eval slots; *out_n = number
+ * of valid results (clamped top-k, model.py:268).  ORC_INVALID_ARGUMENT when a round scores exactly one
+ * candidate (tf.squeeze -> scalar) or num_scoring_per_level[2] != 1 (assert, :347). */
+int orc_search_eval(const orc_index_t* ix, orc_score_fn score, void* score_ctx,
+                    const int32_t* num_scoring_per_level, const int32_t* top_k_per_level, int topk_eval,
+                    int64_t* out_ids, float* out_scores, int32_t* out_nodes, int32_t* out_n,
+                    int64_t* n_scored_total);
+
 /* convenience: mlp2x512 scorer, batch of queries, nthreads request-parallel workers
  * (one request per core, each request single-threaded, as blaze-benchmark's consumers:
  * blaze-benchmark/benchmark/core/benchmark.cc:126-132).  users [B][d].

@@ -263,6 +263,26 @@ class Index:
             res["trace"] = [(tids[r][:tn[r]].copy(), tsc[r][:tn[r]].copy()) for r in range(5)]
         return res
 
+    def search_eval(self, score_fn, num_scoring_per_level=(3, 1, 1), top_k_per_level=(400, 200, 100), topk_eval=200):
+        """`main.py --job-type test` traversal (model.py:299-362) for one query.
+        score_fn(round, ids ndarray) -> f32 scores.  Returns dict(status, n, ids, scores, nodes, n_scored)."""
+        ns, tk = _c(num_scoring_per_level, np.int32), _c(top_k_per_level, np.int32)
+        k = int(topk_eval)
+        out_ids, out_sc, out_nodes = np.full(k, -1, np.int64), np.zeros(k, np.float32), np.full(k, -1, np.int32)
+
+        def cb(_ctx, rnd, ids_p, n, out_p):
+            ids = np.ctypeslib.as_array(ids_p, shape=(n,)) if n > 0 else np.zeros(0, np.int32)
+            sc = np.asarray(score_fn(rnd, ids.copy()), np.float32)
+            assert sc.shape == (n,), (sc.shape, n)
+            if n > 0:
+                np.ctypeslib.as_array(out_p, shape=(n,))[:] = sc
+
+        cbf = _SCORE_FN(cb)
+        n_out, tot = C.c_int32(0), C.c_int64(0)
+        rc = lib().orc_search_eval(C.byref(self.c), cbf, None, _p(ns), _p(tk), C.c_int(k), _p(out_ids), _p(out_sc),
+                                   _p(out_nodes), C.byref(n_out), C.byref(tot))
+        return dict(status=rc, n=n_out.value, ids=out_ids, scores=out_sc, nodes=out_nodes, n_scored=tot.value)
+
     def search_batch_mlp(self, mlp, users, level_topn, nthreads=0):
         """Request-parallel batch (one request per core).  Returns dict(ids, scores, status, seconds, n_scored)."""
         users = _c(users, np.float32)
