@@ -577,10 +577,28 @@ nann_status nann_search_batch(nann_searcher_t* s, const float* users, int B, con
   };
   auto expand_round = [&](int r, int level, const int32_t* frontier, int64_t f_stride, int f_n) -> nann_status {
     const int threads = 128;
+    // CTA-per-query kernel when the round's expansion (f_n * max_deg ids) and its hash table fit in shared memory
+    static const bool force_warp = [] { const char* e = std::getenv("NANN_EXPAND_WARP"); return e && atoi(e) != 0; }();
+    const int64_t cap = (int64_t)f_n * ix->max_deg[level];
+    int64_t tsize = 1024;
+    while (tsize < cap) tsize <<= 1;
+    if (cap * 4 + tsize * 4 <= 200 * 1024) tsize <<= 1;          // halve the load factor when there is room
+    const int64_t smem = cap * 4 + tsize * 2;
     t_begin(1);
-    NANN_LAUNCH(expand_filter_kernel, (unsigned)ceil_div((int64_t)B * 32, threads), threads, 0, st,
-                ix->nbr_values[level], ix->nbr_rs[level], frontier, f_stride, f_n, s->bitmap, s->n_words,
-                s->cand_ids, s->maxc, s->round_n + r * mb, s->round_exp + r * mb, s->status, B);
+    if (!force_warp && f_n > 0 && f_n <= EFC_MAX_FRONTIER && cap > 0 && cap < 65535 && smem <= 200 * 1024) {
+      static bool attr_set = false;
+      if (!attr_set) {
+        NANN_CUDA(cudaFuncSetAttribute(expand_filter_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+      }
+      NANN_LAUNCH(expand_filter_cta_kernel, (unsigned)B, EFC_THREADS, (size_t)smem, st,
+                  ix->nbr_values[level], ix->nbr_rs[level], frontier, f_stride, f_n, s->bitmap, s->n_words,
+                  s->cand_ids, s->maxc, s->round_n + r * mb, s->round_exp + r * mb, s->status, (int)cap, (int)tsize);
+    } else {
+      NANN_LAUNCH(expand_filter_kernel, (unsigned)ceil_div((int64_t)B * 32, threads), threads, 0, st,
+                  ix->nbr_values[level], ix->nbr_rs[level], frontier, f_stride, f_n, s->bitmap, s->n_words,
+                  s->cand_ids, s->maxc, s->round_n + r * mb, s->round_exp + r * mb, s->status, B);
+    }
     t_end();
     return NANN_OK;
   };

@@ -130,6 +130,144 @@ expand_filter_kernel(const int32_t* __restrict__ nbr_vals, const int64_t* __rest
   if (lane == 0) { out_n[q] = (int32_t)o; out_exp[q] = (int32_t)expanded; }
 }
 
+// ---- batched K3+K4, one CTA per query (the default when a round's expansion fits in shared memory) ----------
+// The warp-per-query kernel above is a chain of dependent L2 round trips (~1100 cycles per 32 ids, 0.2 ms per
+// level-0 round at batch 256).  The same result can be computed in parallel: an id is kept iff it was not
+// visited before the round AND it is the FIRST occurrence in the concatenated list, and the output is the kept ids
+// in list order.  So: stage the round's ids in shared memory, find the minimum position of every unvisited id with
+// a shared-memory hash table (open addressing; an entry holds a position, its key is ids[position]; CAS to claim,
+// CAS-min to lower), then compact "position == minimum position of my id" in list order with a block scan and set
+// the visited bits.  Bit-identical to the serial loop (GroupGather_kernel.cc:136-170 + bitmap_ops.cc:221-234).
+constexpr int EFC_THREADS = 512;
+constexpr int EFC_MAX_FRONTIER = 1024;
+constexpr uint32_t EFC_SKIP = 0x80000000u;        // flag on a staged id: visited before the round / out of range
+
+__device__ __forceinline__ int efc_block_scan(int v, int* s_warp, int* tot) {   // exclusive scan over EFC_THREADS threads
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int incl = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += t; }
+  if (lane == 31) s_warp[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    int w = lane < EFC_THREADS / 32 ? s_warp[lane] : 0;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(FULL, w, d); if (lane >= d) w += t; }
+    s_warp[lane] = w;
+  }
+  __syncthreads();
+  const int before = wid > 0 ? s_warp[wid - 1] : 0;
+  *tot = s_warp[EFC_THREADS / 32 - 1];
+  __syncthreads();
+  return before + incl - v;
+}
+
+__global__ void __launch_bounds__(EFC_THREADS)
+expand_filter_cta_kernel(const int32_t* __restrict__ nbr_vals, const int64_t* __restrict__ nbr_rs,
+                         const int32_t* __restrict__ frontier, int64_t f_stride, int f_n,
+                         uint32_t* __restrict__ bitmap, int64_t n_words, int32_t* __restrict__ out_ids,
+                         int64_t out_stride, int32_t* __restrict__ out_n, int32_t* __restrict__ out_exp,
+                         const int32_t* __restrict__ status, int cap, int tsize) {
+  extern __shared__ uint32_t efc_smem[];
+  uint32_t* ids = efc_smem;                                  // [cap] staged ids (| EFC_SKIP)
+  unsigned short* tab = (unsigned short*)(ids + cap);        // [tsize] min position per distinct unvisited id, 0xFFFF = empty
+  __shared__ int s_off[EFC_MAX_FRONTIER + 1];
+  __shared__ long long s_row[EFC_MAX_FRONTIER];
+  __shared__ int s_warp[32];
+  const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (status[q] != 0) {
+    if (tid == 0) { out_n[q] = 0; out_exp[q] = 0; }
+    return;
+  }
+  uint32_t* bm = bitmap + (int64_t)q * n_words;
+  int32_t* out = out_ids + (int64_t)q * out_stride;
+  const int32_t* fr = frontier + (int64_t)q * f_stride;
+  // ---- row bounds of the frontier nodes -> exclusive offsets of their neighbour lists in the concatenation
+  int total = 0;
+  for (int base = 0; base < f_n; base += EFC_THREADS) {
+    const int i = base + tid;
+    int len = 0;
+    if (i < f_n) {
+      const int32_t node = fr[i];
+      const long long s = nbr_rs[node];
+      len = (int)(nbr_rs[node + 1] - s);
+      s_row[i] = s;
+    }
+    int chunk_tot;
+    const int ex = efc_block_scan(len, s_warp, &chunk_tot);
+    if (i < f_n) s_off[i] = total + ex;
+    total += chunk_tot;
+  }
+  if (tid == 0) s_off[f_n] = total;
+  for (int i = tid; i < tsize; i += EFC_THREADS) tab[i] = 0xFFFFu;
+  __syncthreads();
+  if (total > cap) __trap();                                 // the host sized cap from f_n * max_deg
+  // ---- stage the ids (one warp per frontier node) and test them against the bitmap as it is before the round
+  for (int i = wid; i < f_n; i += EFC_THREADS / 32) {
+    const int o = s_off[i], len = s_off[i + 1] - o;
+    const long long s = s_row[i];
+    for (int j = lane; j < len; j += 32) {
+      const int32_t v = nbr_vals[s + j];
+      uint32_t e = (uint32_t)v;
+      if (v < 0 || (int64_t)(v >> 5) >= n_words) e = EFC_SKIP;
+      else if (ld_cg_u32(bm + (v >> 5)) & (1u << (v & 31))) e |= EFC_SKIP;
+      ids[o + j] = e;
+    }
+  }
+  __syncthreads();
+  const uint32_t tmask = (uint32_t)tsize - 1u;
+  auto slot_of = [&](uint32_t v) { return (v * 2654435761u) >> 7 & tmask; };
+  // ---- minimum position per id
+  for (int p = tid; p < total; p += EFC_THREADS) {
+    const uint32_t v = ids[p];
+    if (v & EFC_SKIP) continue;
+    uint32_t h = slot_of(v);
+    for (;;) {
+      unsigned short cur = *(volatile unsigned short*)(tab + h);
+      if (cur == 0xFFFFu) {
+        cur = atomicCAS(tab + h, (unsigned short)0xFFFFu, (unsigned short)p);
+        if (cur == 0xFFFFu) break;                           // claimed the slot for this id
+      }
+      if (ids[cur] == v) {                                   // the slot's key is this id (its position may still drop)
+        while ((int)cur > p) {
+          const unsigned short old = atomicCAS(tab + h, cur, (unsigned short)p);
+          if (old == cur) break;
+          cur = old;
+        }
+        break;
+      }
+      h = (h + 1) & tmask;
+    }
+  }
+  __syncthreads();
+  // ---- first occurrences in list order -> output; visited bits
+  int o = 0;
+  for (int base = 0; base < total; base += EFC_THREADS) {
+    const int p = base + tid;
+    bool keep = false;
+    uint32_t v = 0;
+    if (p < total) {
+      v = ids[p];
+      if (!(v & EFC_SKIP)) {
+        uint32_t h = slot_of(v);
+        for (;;) {
+          const unsigned short cur = tab[h];
+          if (ids[cur] == v) { keep = (int)cur == p; break; }
+          h = (h + 1) & tmask;
+        }
+      }
+    }
+    int chunk_tot;
+    const int rank = efc_block_scan(keep ? 1 : 0, s_warp, &chunk_tot);
+    if (keep) {
+      out[o + rank] = (int32_t)v;
+      atomicOr(bm + (v >> 5), 1u << (v & 31));
+    }
+    o += chunk_tot;
+  }
+  if (tid == 0) { out_n[q] = o; out_exp[q] = total; }
+}
+
 // ---- mark: set the bits of list[q][0..n) (set_difference on a list that is already unique:
 // build_opt_graph.py:119-120,132-133).  One thread per (q, i).
 __global__ void mark_kernel(const int32_t* __restrict__ list, int64_t stride, int n,

@@ -152,7 +152,10 @@ class Mlp:
 
     def __del__(self):
         if getattr(self, "h", None):
-            lib().orc_mlp_destroy(C.c_void_p(self.h))
+            try:                      # module globals may already be gone at interpreter shutdown
+                lib().orc_mlp_destroy(C.c_void_p(self.h))
+            except Exception:
+                pass
             self.h = None
 
     def score_def(self, u, x):
