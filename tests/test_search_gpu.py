@@ -244,3 +244,44 @@ def test_tensor_core_scorer_search_parity(nb, oracle, world):
         np.testing.assert_array_equal(got["scores"][q].view(np.uint32), ref["scores"].view(np.uint32))
         overlap += len(set(got["ids"][q].tolist()) & set(exact["ids"][q].tolist()))
     assert overlap >= 0.99 * 16 * T[5]
+
+
+def _adversarial_index(n=3000, seed=11):
+    """A graph built to stress the visited filter: heavy duplication inside and across neighbour lists (every list
+    draws from a small hub set, with repeats), empty rows, and lists that are entirely visited after one round."""
+    rng = np.random.default_rng(seed)
+    hubs = rng.choice(n, 90, replace=False)
+    vals, rs = [[], []], [[0], [0]]
+    for l, deg in ((0, 64), (1, 32)):
+        for i in range(n):
+            k = 0 if i % 17 == 0 else int(rng.integers(1, deg + 1))
+            row = np.where(rng.random(k) < 0.8, rng.choice(hubs, k), rng.integers(0, n, k))
+            if k > 3:
+                row[1] = row[0]                      # duplicates inside one list
+            vals[l].extend(row.tolist())
+            rs[l].append(len(vals[l]))
+    emb = (rng.standard_normal((n, 128)) / 11.3).astype(np.float32)
+    return dict(emb=emb, item_ids=rng.permutation(n).astype(np.int64), ep=np.sort(rng.choice(n, 120, replace=False)).astype(np.int64),
+                values=[np.asarray(v, np.int64) for v in vals], row_splits=[np.asarray(r, np.int64) for r in rs])
+
+
+def test_expand_filter_cta_kernel_on_adversarial_graph(nb, oracle, world):
+    """The CTA-per-query expand+filter (shared-memory min-position hash) against the oracle's serial loop on a graph
+    with heavy id duplication; bit-exact ids, ranks and scores, and identical per-round candidate counts."""
+    from nann_b200 import scorer_weights as sw
+    w = _adversarial_index()
+    W = sw.mlp_weights(seed=3)
+    ix = nb.Index.from_arrays(w["emb"], w["item_ids"], w["ep"], w["values"], w["row_splits"])
+    sc = nb.Scorer.mlp(*W)
+    T = [40, 60, 60, 60, 60, 100]
+    rng = np.random.default_rng(5)
+    users = (rng.standard_normal((9, 128)) / 11.3).astype(np.float32)
+    got = nb.Searcher(ix, sc, 9, T).search(users, T)
+    oix = oracle.Index(w["emb"], w["item_ids"], w["ep"].astype(np.int32), [v.astype(np.int32) for v in w["values"]], w["row_splits"])
+    want = oix.search_batch_mlp(oracle.Mlp(*W), users, T, nthreads=0)
+    np.testing.assert_array_equal(got["status"], want["status"])
+    ok = want["status"] == 0
+    assert ok.sum() >= 5
+    np.testing.assert_array_equal(got["ids"][ok], want["ids"][ok])
+    np.testing.assert_array_equal(got["scores"][ok].view(np.uint32), want["scores"][ok].view(np.uint32))
+    assert got["n_scored"].sum() == want["n_scored"]
