@@ -586,11 +586,8 @@ nann_status nann_search_batch(nann_searcher_t* s, const float* users, int B, con
     const int64_t smem = cap * 4 + tsize * 2;
     t_begin(1);
     if (!force_warp && f_n > 0 && f_n <= EFC_MAX_FRONTIER && cap > 0 && cap < 65535 && smem <= 200 * 1024) {
-      static bool attr_set = false;
-      if (!attr_set) {
-        NANN_CUDA(cudaFuncSetAttribute(expand_filter_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
-      }
+      // per device, so set on every call (a process may hold searchers on several GPUs); it is a cheap driver call
+      NANN_CUDA(cudaFuncSetAttribute(expand_filter_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       NANN_LAUNCH(expand_filter_cta_kernel, (unsigned)B, EFC_THREADS, (size_t)smem, st,
                   ix->nbr_values[level], ix->nbr_rs[level], frontier, f_stride, f_n, s->bitmap, s->n_words,
                   s->cand_ids, s->maxc, s->round_n + r * mb, s->round_exp + r * mb, s->status, (int)cap, (int)tsize);

@@ -30,9 +30,7 @@ struct MlpTcState {
   float h_b2[MLP_H], h_w3[MLP_H];   // host copies for the by-value kernel parameters
   __half* W1img = nullptr;   // [4 chunks][2 planes][2 slabs][128 rows][64]   swizzled, 256 KB
   __half* W2img = nullptr;   // [8 slabs][2 halves][2 planes][256 rows][64]   swizzled, 1 MB
-  __half* W1img5 = nullptr;
   __half* W8img = nullptr;    // mlp_tc8_kernel: [rank 2][unit 10][hi 32 KB | lo 32 KB], 1.25 MB (scorer_mlp_tc8.cuh)
-  __half* W1img7 = nullptr;          // layer 1 as N=256 units: [(slab*2 + c)][hi 32 KB | lo 32 KB]  // [8 chunks][2 planes][2 slabs][64 rows][64]    swizzled, 256 KB (mlp_tc5_kernel)
   int n_ctas = 0;
 };
 
@@ -54,7 +52,7 @@ static void tc_ws_free(TcWorkspace* ws) {
 static nann_status tc_ws_ensure(TcWorkspace* ws, int n_ctas, int B, int64_t max_tiles) {
   if (ws->n_ctas < n_ctas) {
     cudaFree(ws->scratch); ws->scratch = nullptr; ws->n_ctas = 0;
-    NANN_CUDA(cudaMalloc(&ws->scratch, (size_t)n_ctas * 2 * TC_SCRATCH_BYTES));   // x2: mlp_tc7_kernel keeps two tiles in flight
+    NANN_CUDA(cudaMalloc(&ws->scratch, (size_t)n_ctas * TC_SCRATCH_BYTES));
     ws->n_ctas = n_ctas;
   }
   if (ws->b_cap < B) {
@@ -279,7 +277,7 @@ struct MlpTcArgs {
   const float* table; const int32_t* ids; int64_t ids_stride; int64_t rows_stride;
   const int32_t* n_ptr; int n_fixed; int tiles_per_q; int B;
   const float* hu;        // [B][512]
-  const __half* W1img; const __half* W2img; const __half* W1img5; const __half* W1img7; const __half* W8img;
+  const __half* W1img; const __half* W2img; const __half* W8img;
   const float* b2; const float* w3;
   uint8_t* scratch;       // [gridDim.x][TC_SCRATCH_BYTES]
   float* out; int64_t out_stride; const int32_t* status;
@@ -496,8 +494,6 @@ mlp_tc_kernel(MlpTcArgs p) {
 }  // namespace nann
 #include "scorer_mlp_tc2.cuh"
 #include "scorer_mlp_tc3.cuh"
-#include "scorer_mlp_tc5.cuh"
-#include "scorer_mlp_tc7.cuh"
 #include "scorer_mlp_tc8.cuh"
 namespace nann {
 
@@ -528,20 +524,6 @@ __global__ void tc_build_w2_kernel(const float* __restrict__ W2, __half* __restr
   *reinterpret_cast<__half*>((uint8_t*)img + base + 2 * TC_SLAB_BYTES + off) = lo;
 }
 
-// layer 1 as N=256 units for mlp_tc7_kernel: unit (slab, c) = neurons c*256.., k slab*64.. : [hi 32 KB][lo 32 KB]
-__global__ void tc_build_w1_n256_kernel(const float* __restrict__ W1, __half* __restrict__ img) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;   // one per (n, k): 512 x 128
-  if (t >= 512 * 128) return;
-  const int n = t >> 7, k = t & 127;
-  __half hi, lo;
-  split_f16(W1[n * 256 + 128 + k], hi, lo);
-  const int slab = k >> 6, kk = k & 63, c = n >> 8, r = n & 255;
-  const size_t base = ((size_t)(slab * 2 + c)) * TC_B_BYTES;
-  const size_t off = sw128_chunk_off(r, kk >> 3) + (kk & 7) * 2;
-  *reinterpret_cast<__half*>((uint8_t*)img + base + off) = hi;
-  *reinterpret_cast<__half*>((uint8_t*)img + base + 2 * TC_SLAB_BYTES + off) = lo;
-}
-
 static nann_status mlp_tc_prepare(nann_scorer* s) {
   if (s->tc) return NANN_OK;
   NANN_CUDA(cudaSetDevice(s->device));
@@ -563,21 +545,15 @@ static nann_status mlp_tc_prepare(nann_scorer* s) {
   NANN_CUDA(cudaMemcpy2DAsync(W1.d + 128, 256 * 4, tmp.d, 128 * 4, 128 * 4, 512, cudaMemcpyDeviceToDevice, 0));
   NANN_LAUNCH(transpose_kernel, (unsigned)ceil_div(512 * 512, 256), 256, 0, 0, s->W2T, 512, 512, 512, 0, W2.d);
   if (cudaMalloc(&st->W1img, 4 * TC_B_BYTES) != cudaSuccess || cudaMalloc(&st->W2img, 16 * TC_B_BYTES) != cudaSuccess ||
-      cudaMalloc(&st->W1img5, 8 * T5_STAGE) != cudaSuccess || cudaMalloc(&st->W1img7, 4 * TC_B_BYTES) != cudaSuccess ||
       cudaMalloc(&st->W8img, 2 * T8_IMG_BYTES_PER_RANK) != cudaSuccess) {
     cudaGetLastError();
-    cudaFree(st->W1img); cudaFree(st->W2img); cudaFree(st->W1img5); cudaFree(st->W1img7); cudaFree(st->W8img); delete st;
+    cudaFree(st->W1img); cudaFree(st->W2img); cudaFree(st->W8img); delete st;
     return fail(NANN_RESOURCE_EXHAUSTED, "OOM for tensor-core scorer state");
   }
   NANN_LAUNCH(tc_build_w1_kernel, (512 * 128) / 256, 256, 0, 0, W1.d, st->W1img);
   NANN_LAUNCH(tc_build_w2_kernel, (512 * 512) / 256, 256, 0, 0, W2.d, st->W2img);
-  NANN_LAUNCH(tc_build_w1_v5_kernel, (512 * 128) / 256, 256, 0, 0, W1.d, st->W1img5);
-  NANN_LAUNCH(tc_build_w1_n256_kernel, (512 * 128) / 256, 256, 0, 0, W1.d, st->W1img7);
   NANN_LAUNCH(tc_build_w8_kernel, (2 * T8_UNITS * 256 * 64) / 256, 256, 0, 0, W1.d, W2.d, st->W8img);
   NANN_CUDA(cudaFuncSetAttribute(mlp_tc8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T8_SMEM_BYTES));
-  NANN_CUDA(cudaFuncSetAttribute(mlp_tc7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T7_SMEM_BYTES));
-  NANN_CUDA(cudaFuncSetAttribute(mlp_tc5_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, T5_SMEM_BYTES));
-  NANN_CUDA(cudaFuncSetAttribute(mlp_tc5_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, T5_SMEM_BYTES));
   NANN_CUDA(cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
   NANN_CUDA(cudaFuncSetAttribute(mlp_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
   NANN_CUDA(cudaFuncSetAttribute(mlp_tc3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, T3_SMEM_BYTES));
@@ -598,7 +574,7 @@ static nann_status mlp_tc_score(nann_scorer* s, const ScoreCall& c, cudaStream_t
   MlpTcArgs a{};
   a.table = c.table; a.ids = c.ids; a.ids_stride = c.ids_stride; a.rows_stride = c.rows_stride;
   a.n_ptr = c.n_ptr; a.n_fixed = c.n_fixed; a.tiles_per_q = (int)ceil_div(c.max_n, TC_M); a.B = c.B;
-  a.hu = c.hu; a.W1img = st->W1img; a.W2img = st->W2img; a.W1img5 = st->W1img5; a.W1img7 = st->W1img7; a.W8img = st->W8img; a.b2 = s->b2; a.w3 = s->w3;
+  a.hu = c.hu; a.W1img = st->W1img; a.W2img = st->W2img; a.W8img = st->W8img; a.b2 = s->b2; a.w3 = s->w3;
   a.out = c.out; a.out_stride = c.out_stride; a.status = c.status;
   { const char* g = getenv("NANN_TC_GAP"); a.mma_gap = g ? atoi(g) : 0; }
   memcpy(a.b2c, st->h_b2, sizeof(a.b2c));
@@ -609,8 +585,9 @@ static nann_status mlp_tc_score(nann_scorer* s, const ScoreCall& c, cudaStream_t
   a.trace = g_tc_trace;
   // NANN_TC_KERNEL: 1 = bulk-synchronous cp.async kernel, 2 = warp-specialised TMA ring (h1 via L2 scratch),
   // 3 = 2 + dense tile list, 4 = 3 as 2-CTA clusters with multicast weight stages,
-  // 7 = two tiles in flight (layer 1 of tile i overlaps layer 2 of tile i-1, scorer_mlp_tc7.cuh),
-  // 5 = on-chip h1 hand-off, two layer-2 passes (scorer_mlp_tc5.cuh), 6 = 5 as 2-CTA clusters (multicast)
+  // 8 = cluster-pair neuron split with on-chip h1 exchange (scorer_mlp_tc8.cuh, the default).
+  // (v5/v6: layer-1 recompute with on-chip hand-off, v7: two tiles in flight through the L2 scratch -- measured
+  // slower and removed; see DESIGN.md 4.1 and the git history)
   static const int version = [] { const char* e = std::getenv("NANN_TC_KERNEL"); return e ? atoi(e) : 8; }();
   static const int cta_cap = [] { const char* e = std::getenv("NANN_TC_CTAS"); return e ? atoi(e) : 1 << 30; }();   // debug
   const int grid = (int)std::min<int64_t>(std::min(st->n_ctas, cta_cap), n_tiles);
@@ -619,7 +596,6 @@ static nann_status mlp_tc_score(nann_scorer* s, const ScoreCall& c, cudaStream_t
   NANN_LAUNCH(tile_scan_kernel, 1, 1024, 0, stm, c.n_ptr, c.n_fixed, c.status, c.B, c.ws->tile_start);
   NANN_LAUNCH(tile_fill_kernel, c.B, 128, 0, stm, c.ws->tile_start, c.B, c.ws->tiles);
   if (version == 3) { NANN_LAUNCH(mlp_tc3_kernel<1>, grid, T3_THREADS, T3_SMEM_BYTES, stm, a); return NANN_OK; }
-  if (version == 7) { NANN_LAUNCH(mlp_tc7_kernel, grid, T7_THREADS, T7_SMEM_BYTES, stm, a); return NANN_OK; }
   if (version == 8) {   // cluster pairs, both CTAs on the same tile; the two CTAs red.add their partial scores into out
     NANN_CUDA(cudaMemset2DAsync(c.out, (size_t)c.out_stride * sizeof(float), 0, (size_t)c.max_n * sizeof(float), (size_t)c.B, stm));
     cudaLaunchConfig_t cfg8{};
@@ -635,18 +611,16 @@ static nann_status mlp_tc_score(nann_scorer* s, const ScoreCall& c, cudaStream_t
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return NANN_OK;
   }
-  if (version == 5) { NANN_LAUNCH(mlp_tc5_kernel<1>, grid, T5_THREADS, T5_SMEM_BYTES, stm, a); return NANN_OK; }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(st->n_ctas / 2 * 2));   // whole clusters; CTAs without tiles fall through
-  cfg.blockDim = dim3(version == 6 ? T5_THREADS : T3_THREADS);
-  cfg.dynamicSmemBytes = version == 6 ? T5_SMEM_BYTES : T3_SMEM_BYTES;
+  cfg.blockDim = dim3(T3_THREADS);
+  cfg.dynamicSmemBytes = T3_SMEM_BYTES;
   cfg.stream = stm;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  if (version == 6) NANN_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc5_kernel<2>, a));
-  else              NANN_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc3_kernel<2>, a));
+  NANN_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc3_kernel<2>, a));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return NANN_OK;
 }
@@ -661,7 +635,7 @@ namespace nann {
 static void mlp_tc_release(nann_scorer* s) {
   auto* st = (MlpTcState*)s->tc;
   if (!st) return;
-  cudaFree(st->W1img); cudaFree(st->W2img); cudaFree(st->W1img5); cudaFree(st->W1img7); cudaFree(st->W8img);
+  cudaFree(st->W1img); cudaFree(st->W2img); cudaFree(st->W8img);
   delete st;
   s->tc = nullptr;
 }
