@@ -1,0 +1,188 @@
+"""TF-Serving-compatible REST front-end over the batched search, with dynamic batching.
+
+The reference serves `exec.pb` wrapped into a SavedModel whose `serving_default` signature is
+`comm_seq`, `level_topn` -> `top_k` (NANN_impls/nann/delivery/pb_to_saved_model.py:20-46) from the
+`alinann/nann_serving` TF-Serving image (README.md:196-221: REST on 8501, gRPC on 8500), one `session.run`
+per request.  This module keeps that contract on the REST side --
+
+    POST /v1/models/nann:predict
+    {"inputs": {"comm_seq": [[...user floats...]], "level_topn": [100, 200, 200, 200, 200, 200]}}
+      -> {"outputs": [[item ids ...]]}                    (columnar format; a single named output is returned bare)
+    {"instances": [{"comm_seq": [...]} ...], "level_topn": [...]}   is accepted too (row format)
+      -> {"predictions": [[item ids ...], ...]}
+    GET /v1/models/nann  -> model version status
+
+-- and coalesces concurrent requests with the same `level_topn` into ONE nann_search_batch call (up to
+`max_batch_size` users, waiting at most `batch_timeout_us` for a fuller batch: the knobs blaze-benchmark's
+benchmark_conf would carry).  A request whose query fails the way the reference's graph fails (TopKV2 n < k ...)
+gets HTTP 400 with the op's message, as TF-Serving reports an InvalidArgument status.
+
+    python -m nann_b200.serve --embs-dir D/embeddings --index-dir D/index --port 8501
+"""
+import argparse
+import queue
+import threading
+import time
+
+import numpy as np
+
+
+class _Pending:
+    __slots__ = ("users", "topn", "event", "ids", "scores", "status", "error")
+
+    def __init__(self, users, topn):
+        self.users, self.topn = users, tuple(int(t) for t in topn)
+        self.event = threading.Event()
+        self.ids = self.scores = self.status = self.error = None
+
+
+class DynamicBatcher:
+    """backend(users f32[B, uf], level_topn) -> dict(ids i64[B,k], scores f32[B,k], status i32[B]);
+    requests are served in arrival order, one backend call per group of same-`level_topn` requests."""
+
+    def __init__(self, backend, max_batch_size=256, batch_timeout_us=200):
+        self.backend, self.max_batch = backend, int(max_batch_size)
+        self.timeout = batch_timeout_us * 1e-6
+        self.q = queue.Queue()
+        self.batches = []                      # sizes of the backend calls (observability / tests)
+        self._stop = False
+        self._carry = None
+        self.worker = threading.Thread(target=self._run, daemon=True)
+        self.worker.start()
+
+    def submit(self, users, topn):
+        p = _Pending(np.ascontiguousarray(users, np.float32), topn)
+        if p.users.shape[0] > self.max_batch:
+            raise ValueError(f"request carries {p.users.shape[0]} users, max_batch_size is {self.max_batch}")
+        self.q.put(p)
+        p.event.wait()
+        if p.error is not None:
+            raise p.error
+        return p
+
+    def close(self):
+        self._stop = True
+        self.q.put(None)
+        self.worker.join(timeout=5)
+
+    def _next(self, timeout):
+        if self._carry is not None:
+            p, self._carry = self._carry, None
+            return p
+        try:
+            return self.q.get(timeout=timeout) if timeout is not None else self.q.get()
+        except queue.Empty:
+            return None
+
+    def _run(self):
+        while not self._stop:
+            first = self._next(None)
+            if first is None:
+                continue
+            group, n = [first], first.users.shape[0]
+            deadline = time.perf_counter() + self.timeout
+            while n < self.max_batch:
+                remaining = deadline - time.perf_counter()
+                if remaining <= 0 and self.q.empty() and self._carry is None:
+                    break
+                p = self._next(max(remaining, 0.0))     # waits at most until the deadline for a fuller batch
+                if p is None:
+                    break
+                if p.topn != first.topn or n + p.users.shape[0] > self.max_batch:
+                    self._carry = p            # starts the next group
+                    break
+                group.append(p)
+                n += p.users.shape[0]
+            try:
+                res = self.backend(np.concatenate([g.users for g in group], 0), list(first.topn))
+                self.batches.append(n)
+                o = 0
+                for g in group:
+                    m = g.users.shape[0]
+                    g.ids, g.scores, g.status = res["ids"][o:o + m], res["scores"][o:o + m], res["status"][o:o + m]
+                    o += m
+            except Exception as e:               # the whole group failed (bad level_topn, device error ...)
+                for g in group:
+                    g.error = e
+            for g in group:
+                g.event.set()
+
+
+def create_app(backend, user_floats, model_name="nann", max_batch_size=256, batch_timeout_us=200):
+    from fastapi import FastAPI, HTTPException, Request
+
+    app = FastAPI(title="nann-b200 serving")
+    batcher = DynamicBatcher(backend, max_batch_size, batch_timeout_us)
+    app.state.batcher = batcher
+
+    @app.get("/v1/models/{name}")
+    def status(name: str):
+        if name != model_name:
+            raise HTTPException(404, f"Could not find any versions of model {name}")
+        return {"model_version_status": [{"version": "1", "state": "AVAILABLE", "status": {"error_code": "OK", "error_message": ""}}]}
+
+    @app.post("/v1/models/{name}:predict")
+    async def predict(name: str, request: Request):
+        if name != model_name:
+            raise HTTPException(404, f"Servable not found for request: Latest({name})")
+        body = await request.json()
+        try:
+            if "inputs" in body:                 # columnar
+                inp = body["inputs"]
+                users, topn, row_format = inp["comm_seq"], inp["level_topn"], False
+            else:                                # row format: level_topn is shared by the batch
+                users = [i["comm_seq"] for i in body["instances"]]
+                topn = body.get("level_topn", body["instances"][0].get("level_topn"))
+                row_format = True
+            users = np.asarray(users, np.float32).reshape(-1, user_floats)
+            topn = [int(t) for t in np.asarray(topn).reshape(-1)]
+            if len(topn) != 6:
+                raise ValueError("level_topn must have 6 entries")
+        except (KeyError, TypeError, ValueError) as e:
+            raise HTTPException(400, f"Malformed request: {e}")
+        import anyio
+        try:
+            p = await anyio.to_thread.run_sync(batcher.submit, users, topn)
+        except Exception as e:                   # NannError / ValueError from the backend call
+            raise HTTPException(400, str(e))
+        if np.any(p.status != 0):
+            bad = int(np.flatnonzero(p.status != 0)[0])
+            raise HTTPException(400, f"InvalidArgument: query {bad} failed with status {int(p.status[bad])} "
+                                     f"(TopKV2: input must have at least k columns)")
+        return {"predictions": p.ids.tolist()} if row_format else {"outputs": p.ids.tolist()}
+
+    return app
+
+
+def searcher_backend(searcher):
+    """backend over nann_b200.Searcher (one in-flight call at a time: the batcher has a single worker)."""
+    def run(users, topn):
+        return searcher.search(users, topn)
+    return run
+
+
+def main():
+    import uvicorn
+    import nann_b200 as nb
+    from nann_b200 import scorer_weights as sw
+    ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
+    ap.add_argument("--embs-dir", required=True)
+    ap.add_argument("--index-dir", required=True)
+    ap.add_argument("--max-level-topn", default="100,200,400,400,400,200")
+    ap.add_argument("--max-batch-size", type=int, default=256)
+    ap.add_argument("--batch-timeout-us", type=int, default=200)
+    ap.add_argument("--precision", default="tensor", choices=["exact", "tensor"])
+    ap.add_argument("--host", default="0.0.0.0")
+    ap.add_argument("--port", type=int, default=8501)
+    args = ap.parse_args()
+    ix = nb.Index.load(args.embs_dir, args.index_dir)
+    sc = nb.Scorer.mlp(*sw.mlp_weights(seed=3))      # seeded weights: no checkpoint importer yet
+    if args.precision == "tensor":
+        sc.set_precision(nb.SCORER_TENSOR)
+    se = nb.Searcher(ix, sc, args.max_batch_size, [int(t) for t in args.max_level_topn.split(",")])
+    app = create_app(searcher_backend(se), sc.user_floats, max_batch_size=args.max_batch_size, batch_timeout_us=args.batch_timeout_us)
+    uvicorn.run(app, host=args.host, port=args.port, log_level="warning")
+
+
+if __name__ == "__main__":
+    main()
