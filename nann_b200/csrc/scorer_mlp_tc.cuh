@@ -553,7 +553,8 @@ static nann_status mlp_tc_prepare(nann_scorer* s) {
   NANN_LAUNCH(tc_build_w1_kernel, (512 * 128) / 256, 256, 0, 0, W1.d, st->W1img);
   NANN_LAUNCH(tc_build_w2_kernel, (512 * 512) / 256, 256, 0, 0, W2.d, st->W2img);
   NANN_LAUNCH(tc_build_w8_kernel, (2 * T8_UNITS * 256 * 64) / 256, 256, 0, 0, W1.d, W2.d, st->W8img);
-  NANN_CUDA(cudaFuncSetAttribute(mlp_tc8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T8_SMEM_BYTES));
+  NANN_CUDA(cudaFuncSetAttribute(mlp_tc8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T8_SMEM_BYTES));
+  NANN_CUDA(cudaFuncSetAttribute(mlp_tc8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T8_SMEM_BYTES));
   NANN_CUDA(cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
   NANN_CUDA(cudaFuncSetAttribute(mlp_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
   NANN_CUDA(cudaFuncSetAttribute(mlp_tc3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, T3_SMEM_BYTES));
@@ -607,7 +608,8 @@ static nann_status mlp_tc_score(nann_scorer* s, const ScoreCall& c, cudaStream_t
     attr8[0].id = cudaLaunchAttributeClusterDimension;
     attr8[0].val.clusterDim.x = 2; attr8[0].val.clusterDim.y = 1; attr8[0].val.clusterDim.z = 1;
     cfg8.attrs = attr8; cfg8.numAttrs = 1;
-    NANN_CUDA(cudaLaunchKernelEx(&cfg8, mlp_tc8_kernel, a));
+    if (a.trace) NANN_CUDA(cudaLaunchKernelEx(&cfg8, mlp_tc8_kernel<true>, a));    // debug timeline (scripts/tc_timeline.py)
+    else         NANN_CUDA(cudaLaunchKernelEx(&cfg8, mlp_tc8_kernel<false>, a));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return NANN_OK;
   }

@@ -14,7 +14,8 @@
 // The MMA warp sees one uniform stream of 10 "units" per tile, each = one 32-KB A slab x one 64-KB weight unit
 // (hi stage: Ah.Wh + Al.Wh, lo stage: Ah.Wl; 12 MMAs M128 N256 K16 = 1536 tensor cycles):
 //     u = 0,1      A = x slab (k 0..63 / 64..127 of the gathered rows, written by this CTA's gather)   -> D1
-//     u = 2..9     A = h1 slab (j = (u-2)>>1 of owner o = (u-2)&1, i.e. neurons 256o + 64j ..)         -> D2
+//     u = 2..9     A = h1 slab: own js0, own js1, peer js0, peer js1, own js2, own js3, peer js2, peer js3          -> D2
+//                  (own slabs first, so a slab has two units of MMA time to cross DSMEM before the peer needs it)
 // A slabs flow through a 3-slot ring (a_full: 128 thread arrivals, local or remote; a_empty: one multicast
 // tcgen05.commit from EACH CTA's MMA warp, so a producer knows both consumers are done), weights through a
 // 4-stage cp.async.bulk ring fed from a per-rank image that is already in consumption order (640 KB, cyclic).
@@ -53,9 +54,11 @@ struct T8Bars {
   static constexpr int d2_empty = d1_full + 3;   // 256
   static constexpr int count = d1_full + 4;
 };
-// barrier index / parity a producer of unit n waits on before overwriting the slot (n >= T8_NA)
-__device__ __forceinline__ int t8_aempty_idx(uint32_t n) { return T8Bars::a_empty + (int)(n % T8_NA) * 2 + (int)((n / T8_NA - 1) & 1); }
-__device__ __forceinline__ uint32_t t8_aempty_par(uint32_t n) { return ((n / T8_NA - 1) >> 1) & 1; }
+// barrier index / parity of "ring position q has been consumed by BOTH CTAs"
+__device__ __forceinline__ int t8_consumed_idx(uint32_t q) { return T8Bars::a_empty + (int)(q % T8_NA) * 2 + (int)((q / T8_NA) & 1); }
+__device__ __forceinline__ uint32_t t8_consumed_par(uint32_t q) { return ((q / T8_NA) >> 1) & 1; }
+// ring positions 2,3,6,7 of a tile hold this CTA's own h1 slabs (sources of DSMEM copies to the peer's position + 2)
+__device__ __forceinline__ bool t8_is_own_slab(uint32_t q) { const uint32_t u = q % T8_UNITS; return u == 2 || u == 3 || u == 6 || u == 7; }
 
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank) {
   uint32_t r;
@@ -98,14 +101,34 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
   }
 }
 
+// The MMA warp's wait: as few instructions as possible between two units (the tensor core's issue queue is ~2 MMAs
+// = 256 cycles deep; the generic mbar_wait + bookkeeping path was ~130 SASS instructions per unit and left the pipe
+// idle for ~300 cycles per unit).  try_wait with a 1 ms suspend hint; a lost arrival still traps after ~2 s.
+__device__ __forceinline__ void mbar_wait_lean(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile("{\n\t.reg .pred p;\n\t"
+               "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 1000000;\n\t"
+               "selp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  if (done) return;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 1000000;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (spin > 4000) __trap();
+  }
+}
+
+template <bool TRACE>
 __global__ void __launch_bounds__(T8_THREADS, 1)
 mlp_tc8_kernel(MlpTcArgs p) {
   uint32_t rank;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
   const uint32_t peer = rank ^ 1u;
-  long long* const trace = (blockIdx.x == 0) ? p.trace : nullptr;
+  long long* const trace = (TRACE && blockIdx.x == 0) ? p.trace : nullptr;     // TRACE=false: every stamp compiles out
   auto TR = [&](int it_local, int ev) {
-    if (trace && it_local < 60) trace[it_local * 48 + ev] = clock64();
+    if (TRACE && trace && it_local < 60) trace[it_local * 48 + ev] = clock64();
   };
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* smem = tc_smem_raw;
@@ -174,79 +197,75 @@ mlp_tc8_kernel(MlpTcArgs p) {
     }
   } else if (warp == 1) {
     // =============================== MMA issuer (whole warp, elected lane issues) ===============================
-    uint32_t it = 0, n = 0;                                // weight stage counter, A unit counter
+    // D[128 x 256] (+)= A[128 x 64] (hi,lo) * W[256 x 64]^T (hi,lo) per unit: stage "hi" 8 MMAs, stage "lo" 4 MMAs.
+    // Ring positions are kept as incrementing slot/parity pairs (no divisions in the loop).
+    uint32_t w_slot = 0, w_par = 0, a_slot = 0, a_par = 0, ae_sel = 0;   // ae_sel: which of the slot's two a_empty barriers
     long long ring_cyc = 0, afull_cyc = 0;
     const uint32_t idesc = umma_idesc_f16(128, 256);
-    auto ring_wait = [&]() -> uint32_t {
-      const uint32_t slot = it % T8_NW, ph = (it / T8_NW) & 1;
-      const long long w0 = trace ? clock64() : 0;
-      mbar_wait(B(T8Bars::w_full + slot), ph);
-      if (trace) ring_cyc += clock64() - w0;
-      tc_fence_after();
-      return sW_u + slot * T2_STAGE;
-    };
-    // D[128 x 256] (+)= A[128 x 64] (hi,lo) * W[256 x 64]^T (hi,lo): stage "hi" 8 MMAs, stage "lo" 4 MMAs.
-    // (Waiting for the NEXT unit's barriers before the last MMAs of this one -- to hide the poll latency behind
-    // queued MMAs -- was measured slower: the kernel is bound by shared-memory bandwidth, not by issue gaps.)
-    auto unit = [&](uint32_t d, uint32_t first) {
-      const uint32_t slot = n % T8_NA;
-      {
-        const long long w0 = trace ? clock64() : 0;
-        // CTA-scope acquire: the slab is read by the tensor core (async proxy), never by this warp
-        mbar_wait(B(T8Bars::a_full + slot), (n / T8_NA) & 1);
-        if (trace) afull_cyc += clock64() - w0;
-      }
-      tc_fence_after();
-      const bool st11 = trace && lane == 0 && n >= 11 * T8_UNITS && n < 12 * T8_UNITS;   // debug: unit stamps of tile 11
-      long long* const st = trace + 60 * 48 + (st11 ? (n - 11 * T8_UNITS) * 4 : 0);      // rows 60.. (tiles >= 60 do not stamp)
+    const uint64_t dA0 = umma_desc_sw128(sA_u), dW0 = umma_desc_sw128(sW_u);
+    auto w_advance = [&]() { if (++w_slot == T8_NW) { w_slot = 0; w_par ^= 1; } };
+    auto unit = [&](int i, int u, uint32_t d, uint32_t first) {
+      long long w0 = 0;
+      if (TRACE) w0 = clock64();
+      // CTA-scope acquire: the slab is read by the tensor core (async proxy), never by this warp
+      mbar_wait_lean(B(T8Bars::a_full + a_slot), a_par);
+      if (TRACE) { const long long w1 = clock64(); afull_cyc += w1 - w0; w0 = w1; }
+      const bool st11 = TRACE && trace && lane == 0 && i == 11;                 // debug: unit stamps of tile 11
+      long long* const st = trace + 60 * 48 + (st11 ? u * 4 : 0);              // rows 60.. (tiles >= 60 do not stamp)
       if (st11) st[0] = clock64();
-      const uint32_t a_hi = sA_u + slot * T2_STAGE, a_lo = a_hi + TC_SLAB_BYTES;
-      const uint32_t bh = ring_wait();
+      mbar_wait_lean(B(T8Bars::w_full + w_slot), w_par);
+      if (TRACE) ring_cyc += clock64() - w0;
+      tc_fence_after();
       if (st11) st[1] = clock64();
+      // descriptors differ only in their 14-bit address field (bytes >> 4): base + slot * (32 KB >> 4)
+      const uint64_t ah0 = dA0 + (uint64_t)(a_slot * (T2_STAGE >> 4));
       if (elect_one()) {
-        uint64_t ah = umma_desc_sw128(a_hi), al = umma_desc_sw128(a_lo), wh = umma_desc_sw128(bh);
+        uint64_t ah = ah0, al = ah0 + (TC_SLAB_BYTES >> 4), wh = dW0 + (uint64_t)(w_slot * (T2_STAGE >> 4));
 #pragma unroll 1
         for (int ks = 0; ks < 4; ++ks) {
           tc_mma_f16(d, ah, wh, idesc, (first && ks == 0) ? 0u : 1u);
           tc_mma_f16(d, al, wh, idesc, 1u);
           ah += 2; al += 2; wh += 2;
         }
-        tc_commit(B(T8Bars::w_empty + (it % T8_NW)));
+        tc_commit(B(T8Bars::w_empty + w_slot));
       }
-      ++it;
-      const uint32_t bl = ring_wait();
+      w_advance();
+      if (TRACE) w0 = clock64();
+      mbar_wait_lean(B(T8Bars::w_full + w_slot), w_par);
+      if (TRACE) ring_cyc += clock64() - w0;
+      tc_fence_after();
       if (st11) st[2] = clock64();
       if (elect_one()) {
-        uint64_t ah = umma_desc_sw128(a_hi), wl = umma_desc_sw128(bl);
+        uint64_t ah = ah0, wl = dW0 + (uint64_t)(w_slot * (T2_STAGE >> 4));
 #pragma unroll 1
         for (int ks = 0; ks < 4; ++ks) {
           tc_mma_f16(d, ah, wl, idesc, 1u);
           ah += 2; wl += 2;
         }
-        tc_commit(B(T8Bars::w_empty + (it % T8_NW)));
-        tc_commit_mc(B(T8Bars::a_empty + slot * 2 + ((n / T8_NA) & 1)), (uint16_t)3);   // slab consumed: tell the producers of BOTH CTAs
+        tc_commit(B(T8Bars::w_empty + w_slot));
+        tc_commit_mc(B(T8Bars::a_empty + a_slot * 2 + ae_sel), (uint16_t)3);   // slab consumed: tell the producers of BOTH CTAs
+        if (u == 1) tc_commit(B(T8Bars::d1_full));
+        if (u == T8_UNITS - 1) tc_commit(B(T8Bars::d2_full));
       }
       if (st11) st[3] = clock64();
-      ++it;
-      ++n;
+      w_advance();
+      if (++a_slot == T8_NA) { a_slot = 0; a_par ^= 1; ae_sel ^= 1; }
     };
     for (int i = 0; i < my; ++i) {
       if (lane == 0) TR(i, 0);
-      if (i > 0) { mbar_wait(B(T8Bars::d1_empty), (i - 1) & 1); tc_fence_after(); }
-      unit(tmem_d1, 1u);
-      unit(tmem_d1, 0u);
-      if (elect_one()) tc_commit(B(T8Bars::d1_full));
+      if (i > 0) mbar_wait_lean(B(T8Bars::d1_empty), (i - 1) & 1);
+      unit(i, 0, tmem_d1, 1u);
+      unit(i, 1, tmem_d1, 0u);
       if (lane == 0) TR(i, 1);
-      if (i > 0) { mbar_wait(B(T8Bars::d2_empty), (i - 1) & 1); tc_fence_after(); }
+      if (i > 0) mbar_wait_lean(B(T8Bars::d2_empty), (i - 1) & 1);
       if (lane == 0) TR(i, 2);
 #pragma unroll 1
       for (int u = 2; u < T8_UNITS; ++u) {
-        unit(tmem_d2, u == 2 ? 1u : 0u);
-        if (lane == 0 && u < 6) TR(i, 1 + u);              // events 3..6: units 2..5 issued
+        unit(i, u, tmem_d2, u == 2 ? 1u : 0u);
+        if (TRACE && lane == 0 && u < 6) TR(i, 1 + u);    // events 3..6: units 2..5 issued
       }
-      if (elect_one()) tc_commit(B(T8Bars::d2_full));
       if (lane == 0) TR(i, 7);
-      if (trace && lane == 0 && i < 60) { trace[i * 48 + 46] = ring_cyc; trace[i * 48 + 47] = afull_cyc; }
+      if (TRACE && trace && lane == 0 && i < 60) { trace[i * 48 + 46] = ring_cyc; trace[i * 48 + 47] = afull_cyc; }
       ring_cyc = 0; afull_cyc = 0;
     }
   } else {
@@ -275,30 +294,35 @@ mlp_tc8_kernel(MlpTcArgs p) {
         v[jj] = ld_row16(p.table + ridx * MLP_D + lane * 4);
       }
     };
-    // ---- x slabs of tile j: units 10j (k 0..63, lanes 0..15) and 10j+1 (k 64..127, lanes 16..31)
+    // ---- x slabs of tile j: units 10j (k 0..63, lanes 0..15) and 10j+1 (k 64..127, lanes 16..31).
+    // A slot that held one of this CTA's own h1 slabs is also the SOURCE of the DSMEM copy to the peer: it may be
+    // overwritten only once the peer has consumed the copy (then it has certainly been read out).
     auto x_write = [&](int j, const float4 (&v)[ROWS_PER_WARP]) {
       const uint32_t n0 = (uint32_t)j * T8_UNITS;
-      if (n0 >= T8_NA) {
-        mbar_wait(B(t8_aempty_idx(n0)), t8_aempty_par(n0));
-        mbar_wait(B(t8_aempty_idx(n0 + 1)), t8_aempty_par(n0 + 1));
-      }
-      const uint32_t nn = n0 + (lane >> 4);
-      uint8_t* dst = sA + (nn % T8_NA) * T2_STAGE;
       const int k = (lane & 15) * 4, chunk = k >> 3, sub = (k & 7) * 2;
 #pragma unroll
-      for (int jj = 0; jj < ROWS_PER_WARP; ++jj) {
-        const int c = ew * ROWS_PER_WARP + jj;
-        uint32_t h01, l01, h23, l23;
-        split2_f16(v[jj].x, v[jj].y, h01, l01); split2_f16(v[jj].z, v[jj].w, h23, l23);
-        const uint32_t off = sw128_chunk_off(c, chunk) + sub;
-        *reinterpret_cast<uint2*>(dst + off) = make_uint2(h01, h23);
-        *reinterpret_cast<uint2*>(dst + TC_SLAB_BYTES + off) = make_uint2(l01, l23);
-      }
-      fence_proxy_async();
-      asm volatile("bar.sync 1, %0;" ::"n"(T2_EPI_THREADS) : "memory");
-      if (ew == 0 && lane == 0) {
-        mbar_arrive(B(T8Bars::a_full + n0 % T8_NA));
-        mbar_arrive(B(T8Bars::a_full + (n0 + 1) % T8_NA));
+      for (int half = 0; half < 2; ++half) {
+        const uint32_t nn = n0 + half;
+        if (nn >= T8_NA) {
+          const uint32_t m = nn - T8_NA;                      // previous occupant of the slot
+          const uint32_t q = t8_is_own_slab(m) ? m + 2 : m;   // an own slab is free once the peer consumed its copy
+          mbar_wait(B(t8_consumed_idx(q)), t8_consumed_par(q));
+        }
+        if ((lane >> 4) == half) {
+          uint8_t* dst = sA + (nn % T8_NA) * T2_STAGE;
+#pragma unroll
+          for (int jj = 0; jj < ROWS_PER_WARP; ++jj) {
+            const int c = ew * ROWS_PER_WARP + jj;
+            uint32_t h01, l01, h23, l23;
+            split2_f16(v[jj].x, v[jj].y, h01, l01); split2_f16(v[jj].z, v[jj].w, h23, l23);
+            const uint32_t off = sw128_chunk_off(c, chunk) + sub;
+            *reinterpret_cast<uint2*>(dst + off) = make_uint2(h01, h23);
+            *reinterpret_cast<uint2*>(dst + TC_SLAB_BYTES + off) = make_uint2(l01, l23);
+          }
+        }
+        fence_proxy_async();
+        asm volatile("bar.sync 1, %0;" ::"n"(T2_EPI_THREADS) : "memory");
+        if (ew == 0 && lane == 0) mbar_arrive(B(T8Bars::a_full + nn % T8_NA));
       }
     };
     // ---- epilogue 1 of tile j: ALL eight warps build every slab (own neurons js*64 ..: this warp's 32 rows x the
@@ -311,9 +335,18 @@ mlp_tc8_kernel(MlpTcArgs p) {
       const uint32_t tb = tmem_d1 + t_lane + (uint32_t)(col_half * 32);
       tc_ld32_nowait(tb, va);
       auto slab = [&](uint32_t (&v)[32], uint32_t (&vnext)[32], int js) {
-        const uint32_t n = (uint32_t)j * T8_UNITS + 2 + 2 * js + rank;     // its unit number
-        const uint32_t slot = n % T8_NA;
-        if (n >= T8_NA) mbar_wait(B(t8_aempty_idx(n)), t8_aempty_par(n));  // both CTAs consumed the slot's previous slab
+        // Each CTA consumes two OWN slabs before the peer's two (unit order x0 x1 | own0 own1 peer0 peer1 | own2 own3
+        // peer2 peer3), so a slab has ~3k cycles of MMA work to cross DSMEM (32 KB take 2-3k cycles) before the peer
+        // needs it.  The same slab therefore sits at ring position n in this CTA and n + 2 in the peer's.
+        const uint32_t n = (uint32_t)j * T8_UNITS + 2 + (uint32_t)((js >> 1) * 4 + (js & 1));
+        const uint32_t nr = n + 2;
+        const uint32_t slot = n % T8_NA, rslot = nr % T8_NA;
+        // a_empty barriers collect the multicast commits of BOTH CTAs for a ring position: position n - NA frees the
+        // local slot, position nr - NA the peer's
+        // (if the local slot's previous occupant was an own slab too, its copy sits at the peer's position
+        // n - NA + 2 = nr - NA: the second wait covers that as well)
+        if (n >= T8_NA) mbar_wait(B(t8_consumed_idx(n - T8_NA)), t8_consumed_par(n - T8_NA));
+        if (nr >= T8_NA) mbar_wait(B(t8_consumed_idx(nr - T8_NA)), t8_consumed_par(nr - T8_NA));
         uint8_t* dl = sA + slot * T2_STAGE;
         tc_ld_wait_dep(v);
         if (js < 3) tc_ld32_nowait(tb + (uint32_t)((js + 1) * 64), vnext);
@@ -339,8 +372,8 @@ mlp_tc8_kernel(MlpTcArgs p) {
         asm volatile("bar.sync 1, %0;" ::"n"(T2_EPI_THREADS) : "memory");
         if (ew == 0 && lane == 0) {
           mbar_arrive(B(T8Bars::a_full + slot));
-          const uint32_t rb = rbar0 + 8u * (uint32_t)(T8Bars::a_full + slot);
-          const uint32_t src = sA_u + slot * T2_STAGE, dst = rA_u + slot * T2_STAGE;
+          const uint32_t rb = rbar0 + 8u * (uint32_t)(T8Bars::a_full + rslot);
+          const uint32_t src = sA_u + slot * T2_STAGE, dst = rA_u + rslot * T2_STAGE;
           mbar_expect_tx_remote(rb, T2_STAGE);
           bulk_s2peer(dst, src, TC_SLAB_BYTES, rb);
           bulk_s2peer(dst + TC_SLAB_BYTES, src + TC_SLAB_BYTES, TC_SLAB_BYTES, rb);
@@ -438,7 +471,10 @@ __global__ void tc_build_w8_kernel(const float* __restrict__ W1, const float* __
   const int nrn = 256 * r + rowi;
   float w;
   if (u < 2) w = W1[nrn * 256 + 128 + 64 * u + kk];
-  else { const int j = (u - 2) >> 1, o = (u - 2) & 1; w = W2[nrn * 512 + 256 * o + 64 * j + kk]; }
+  else {   // unit order of rank r: own js0, own js1, peer js0, peer js1, own js2, own js3, peer js2, peer js3
+    const int idx = u - 2, js = (idx >> 2) * 2 + (idx & 1), o = (idx & 2) ? 1 - r : r;
+    w = W2[nrn * 512 + 256 * o + 64 * js + kk];
+  }
   __half hi, lo;
   split_f16(w, hi, lo);
   const size_t base = ((size_t)(r * T8_UNITS + u) * 2) * T2_STAGE;
