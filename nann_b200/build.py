@@ -39,7 +39,8 @@ def build(force=False, verbose=False):
     if not force and not is_stale():
         return LIB
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+    extra = os.environ.get("NANN_NVCC_EXTRA", "").split()      # e.g. -DNANN_T8_COPY_CHUNK=4096 for A/B builds
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
           ["-o", LIB, os.path.join(CSRC, "nann_b200.cu")]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

@@ -375,8 +375,11 @@ mlp_tc8_kernel(MlpTcArgs p) {
           const uint32_t rb = rbar0 + 8u * (uint32_t)(T8Bars::a_full + rslot);
           const uint32_t src = sA_u + slot * T2_STAGE, dst = rA_u + rslot * T2_STAGE;
           mbar_expect_tx_remote(rb, T2_STAGE);
-          bulk_s2peer(dst, src, TC_SLAB_BYTES, rb);
-          bulk_s2peer(dst + TC_SLAB_BYTES, src + TC_SLAB_BYTES, TC_SLAB_BYTES, rb);
+#ifndef NANN_T8_COPY_CHUNK
+#define NANN_T8_COPY_CHUNK 16384
+#endif
+#pragma unroll
+          for (uint32_t o = 0; o < (uint32_t)T2_STAGE; o += NANN_T8_COPY_CHUNK) bulk_s2peer(dst + o, src + o, NANN_T8_COPY_CHUNK, rb);
         }
       };
       slab(va, vb, 0);
