@@ -176,7 +176,7 @@ def main():
     ap.add_argument("--port", type=int, default=8501)
     args = ap.parse_args()
     ix = nb.Index.load(args.embs_dir, args.index_dir)
-    sc = nb.Scorer.mlp(*sw.mlp_weights(seed=3))      # seeded weights: no checkpoint importer yet
+    sc = nb.Scorer.mlp(*sw.mlp_weights(seed=3))      # seeded mlp2x512 weights (the bench scorer); see tf_import.py for frozen graphs
     if args.precision == "tensor":
         sc.set_precision(nb.SCORER_TENSOR)
     se = nb.Searcher(ix, sc, args.max_batch_size, [int(t) for t in args.max_level_topn.split(",")])
