@@ -285,3 +285,62 @@ def test_expand_filter_cta_kernel_on_adversarial_graph(nb, oracle, world):
     np.testing.assert_array_equal(got["ids"][ok], want["ids"][ok])
     np.testing.assert_array_equal(got["scores"][ok].view(np.uint32), want["scores"][ok].view(np.uint32))
     assert got["n_scored"].sum() == want["n_scored"]
+
+
+def test_mid_size_corpus_large_ragged_batch(nb, oracle):
+    """40 k items (M=32 like the bench), ef=400-shaped beam widths, a batch of 300 (not a power of two, several waves of
+    CTAs per kernel): every query of the batch is checked bit-exact against the oracle in EXACT mode; the tensor-core
+    path returns the same items up to near-tie flips."""
+    from tests import util
+    from nann_b200 import scorer_weights as sw
+    w = util.build_world(40000, M=32, m_levels=32, seed=4, device="cuda", tag="mid")
+    W = sw.mlp_weights(seed=3)
+    T = [30, 120, 240, 240, 240, 200]
+    from nann_b200 import index as nix
+    users = nix.synthetic_queries(w["emb"], 300, seed=7)
+    ix = nb.Index.from_arrays(w["emb"], w["item_ids"], w["ep"], w["values"], w["row_splits"])
+    sc = nb.Scorer.mlp(*W)
+    se = nb.Searcher(ix, sc, 300, T)
+    got = se.search(users, T)
+    import os
+    want = util.oracle_index(oracle, w).search_batch_mlp(oracle.Mlp(*W), users, T, nthreads=min(16, os.cpu_count() or 1))
+    np.testing.assert_array_equal(got["status"], want["status"])
+    assert np.all(want["status"] == 0)
+    np.testing.assert_array_equal(got["ids"], want["ids"])
+    np.testing.assert_array_equal(got["scores"].view(np.uint32), want["scores"].view(np.uint32))
+    assert got["n_scored"].sum() == want["n_scored"]
+    sc.set_precision(nb.SCORER_TENSOR)
+    tens = se.search(users, T)
+    assert np.all(tens["status"] == 0)
+    overlap = np.mean([len(set(a.tolist()) & set(b.tolist())) / T[5] for a, b in zip(tens["ids"], want["ids"])])
+    assert overlap >= 0.995
+
+
+def test_two_shards_on_one_device_merge_like_the_oracle(nb, oracle, world):
+    """Row-sharded search in one process: two shards of the small corpus with their own HNSW, per-shard
+    beams, nann_merge_topk; the merged result equals the stable merge (score desc, ties -> lower shard, then rank)
+    of the per-shard ORACLE results."""
+    from nann_b200 import index as nix
+    from nann_b200.distributed import shard_bounds, shard_level_topn
+    T = world["T"]
+    Ts = shard_level_topn(T, 2)
+    users = world["queries"][:8]
+    sc_l, id_l, osc_l, oid_l = [], [], [], []
+    for r in range(2):
+        lo, hi = shard_bounds(world["emb"].shape[0], 2, r)
+        emb, ids = world["emb"][lo:hi], world["item_ids"][lo:hi]
+        g = nix.build_hnsw(emb, M=16, m_levels=6, seed=4 + r, n_cand=40, device="cpu")
+        ix = nb.Index.from_arrays(emb, ids, g["enter_points"], g["values"], g["row_splits"])
+        res = nb.Searcher(ix, world["scorer"], 8, Ts).search(users, Ts)
+        assert np.all(res["status"] == 0)
+        sc_l.append(res["scores"]); id_l.append(res["ids"])
+        oix = oracle.Index(emb, ids, g["enter_points"].astype(np.int32), [v.astype(np.int32) for v in g["values"]], g["row_splits"])
+        o = oix.search_batch_mlp(world["omlp"], users, Ts, nthreads=0)
+        osc_l.append(o["scores"]); oid_l.append(o["ids"])
+    m_sc, m_id = nb.merge_topk(np.stack(sc_l), np.stack(id_l), T[5])
+    for q in range(8):
+        cs = np.concatenate([osc_l[0][q], osc_l[1][q]])
+        ci = np.concatenate([oid_l[0][q], oid_l[1][q]])
+        o = np.argsort(-cs, kind="stable")[:T[5]]
+        np.testing.assert_array_equal(m_id[q], ci[o])
+        np.testing.assert_array_equal(m_sc[q].view(np.uint32), cs[o].view(np.uint32))
