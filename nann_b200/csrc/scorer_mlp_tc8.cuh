@@ -8,17 +8,19 @@
 // 10.8k of its 50.9k cycles per tile) and serialises layer 1 -> epilogue -> layer 2.  Splitting the NEURONS over
 // two CTAs halves every accumulator: CTA r keeps D1 = x.W1x[256r..256r+255]^T (TMEM columns 256..511) and
 // D2 = h1.W2[256r..256r+255]^T (columns 0..255).  Layer 2 needs all 512 h1 values as its K dimension, so each
-// CTA converts its 256 h1 columns into four 64-k slabs ((hi,lo) fp16, UMMA K-major SWIZZLE_128B) and writes every
-// slab into BOTH CTAs' shared memory (st.shared + st.shared::cluster), where it lives only until its 12 MMAs ran.
+// CTA converts its 256 h1 columns into four 64-k slabs ((hi,lo) fp16, UMMA K-major SWIZZLE_128B), written into its own
+// shared memory with st.shared and shipped to the peer's with DSMEM bulk copies (cp.async.bulk.shared::cluster
+// .shared::cta, completion on the peer's mbarrier); a slab lives only until its 12 MMAs ran.
 //
 // The MMA warp sees one uniform stream of 10 "units" per tile, each = one 32-KB A slab x one 64-KB weight unit
 // (hi stage: Ah.Wh + Al.Wh, lo stage: Ah.Wl; 12 MMAs M128 N256 K16 = 1536 tensor cycles):
 //     u = 0,1      A = x slab (k 0..63 / 64..127 of the gathered rows, written by this CTA's gather)   -> D1
 //     u = 2..9     A = h1 slab: own js0, own js1, peer js0, peer js1, own js2, own js3, peer js2, peer js3          -> D2
 //                  (own slabs first, so a slab has two units of MMA time to cross DSMEM before the peer needs it)
-// A slabs flow through a 3-slot ring (a_full: 128 thread arrivals, local or remote; a_empty: one multicast
-// tcgen05.commit from EACH CTA's MMA warp, so a producer knows both consumers are done), weights through a
-// 4-stage cp.async.bulk ring fed from a per-rank image that is already in consumption order (640 KB, cyclic).
+// A slabs flow through a 4-slot ring (a_full: one arrival, plus 32 KB of complete_tx for a peer slab; a_empty: one
+// multicast tcgen05.commit from EACH CTA's MMA warp, so a producer knows both consumers are done with a ring
+// position), weights through a 3-stage cp.async.bulk ring fed from a per-rank image that is already in consumption
+// order (640 KB, cyclic).  7 x 32 KB + 3 KB = all 227 KB of shared memory.
 // Per tile and CTA: 120 MMAs = 15.4k tensor cycles for 128 rows per PAIR = the 30.7k-cycle/SM floor of the 3-MMA split.
 //
 // Epilogue warps (8) per tile i:  epi1(i): D1 -> +hu, relu, split -> slabs (local + remote)
