@@ -192,7 +192,12 @@ mlp_tc8_kernel(MlpTcArgs p) {
         mbar_wait(B(T8Bars::w_empty + slot), ph ^ 1);
         if (elect_one()) {
           mbar_expect_tx(B(T8Bars::w_full + slot), T2_STAGE);
-          bulk_g2s(sW_u + slot * T2_STAGE, img + (size_t)st * T2_STAGE, T2_STAGE, B(T8Bars::w_full + slot));
+#ifndef NANN_T8_W_CHUNK
+#define NANN_T8_W_CHUNK 32768
+#endif
+#pragma unroll
+          for (uint32_t o = 0; o < (uint32_t)T2_STAGE; o += NANN_T8_W_CHUNK)
+            bulk_g2s(sW_u + slot * T2_STAGE + o, img + (size_t)st * T2_STAGE + o, NANN_T8_W_CHUNK, B(T8Bars::w_full + slot));
         }
         ++it;
       }
