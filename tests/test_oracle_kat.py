@@ -182,6 +182,71 @@ def test_search_stats_and_shapes(oracle, small_world):
     np.testing.assert_array_equal(b["scores"][3].view(np.uint32), res["scores"].view(np.uint32))
 
 
+def _exec_pb_numpy(w, score, T):
+    """build_opt_graph.py:109-149 written with numpy primitives only (independent of the C oracle): ragged gather =
+    concatenation of CSR rows in frontier order, set_difference = first occurrence not yet flagged, top_k = stable
+    descending argsort (TopKV2's tie rule)."""
+    nbr = [(w["values"][l], w["row_splits"][l]) for l in range(2)]
+
+    def expand(level, ids):
+        v, rs = nbr[level]
+        return np.concatenate([v[rs[i]:rs[i + 1]] for i in ids]) if len(ids) else np.zeros(0, np.int64)
+
+    def diff(ids, flags):
+        out = []
+        for v in ids:                                   # bitmap_ops.cc:221-234: keep iff bit unset, then set it
+            if not flags[v]:
+                flags[v] = True
+                out.append(v)
+        return np.asarray(out, np.int64)
+
+    def topk(ids, sc, k):
+        assert len(ids) >= k
+        o = np.argsort(-sc, kind="stable")[:k]
+        return ids[o], sc[o]
+
+    n = w["emb"].shape[0]
+    ep = w["ep"].astype(np.int64)
+    R, Rs = topk(ep, score(ep), T[0])                                    # level 2   :109-112
+    N1 = expand(1, R)                                                    # level 1   :114-127
+    flags = np.zeros(n, bool)
+    R = diff(R, flags)
+    N1 = diff(N1, flags)
+    s1 = score(N1)
+    R, Rs = topk(np.concatenate([R, N1]), np.concatenate([Rs, s1]), T[1])
+    flags = np.zeros(n, bool)                                            # level 0   :128-141 (visited set reset)
+    C = diff(R.copy(), flags)
+    for i in range(3):
+        Nx = diff(expand(0, C), flags)
+        sx = score(Nx)
+        C, Cs = topk(Nx, sx, T[i + 2])
+        R, Rs = np.concatenate([R, C]), np.concatenate([Rs, Cs])
+    R, Rs = topk(R, Rs, T[5])                                            # :143-144
+    return w["item_ids"][R], Rs
+
+
+def test_search_matches_numpy_restatement(oracle, small_world):
+    """Pins orc_search (the whole exec.pb dataflow, not just its ops) against an independent numpy restatement, with
+    the mlp scorer and with a scorer full of ties (scores rounded to one decimal: exercises both tie rules --
+    position in the concatenated list, old results before new ones)."""
+    from tests import util
+    w = small_world
+    ix = util.oracle_index(oracle, w)
+    m = oracle.Mlp(*w["mlp"])
+    for T in (w["T"], [30, 45, 20, 70, 25, 60]):
+        for q in (1, 9):
+            u = w["queries"][q]
+            for tie in (False, True):
+                def score(ids, u=u, tie=tie):
+                    s = m.score(u, w["emb"], np.asarray(ids, np.int32)) if len(ids) else np.zeros(0, np.float32)
+                    return np.round(s, 1).astype(np.float32) if tie else s
+                want_ids, want_sc = _exec_pb_numpy(w, score, T)
+                got = ix.search(lambda r, ids: score(ids), T)
+                assert got["status"] == oracle.OK
+                np.testing.assert_array_equal(got["ids"], want_ids)
+                np.testing.assert_array_equal(got["scores"].view(np.uint32), want_sc.view(np.uint32))
+
+
 def test_search_error_when_fewer_than_k(oracle, small_world):
     from tests import util
     ix = util.oracle_index(oracle, small_world)
