@@ -12,7 +12,9 @@ per request.  This module keeps that contract on the REST side --
       -> {"predictions": [[item ids ...], ...]}
     GET /v1/models/nann  -> model version status
 
--- and coalesces concurrent requests with the same `level_topn` into ONE nann_search_batch call (up to
+and on the gRPC side (`create_grpc_server`: `tensorflow.serving.PredictionService/Predict` with inputs `comm_seq`,
+`level_topn` and output `top_k`, the call of the reference's smoke test; messages are handled at the protobuf wire
+level, no TensorFlow packages needed) -- and coalesces concurrent requests with the same `level_topn` into ONE nann_search_batch call (up to
 `max_batch_size` users, waiting at most `batch_timeout_us` for a fuller batch: the knobs blaze-benchmark's
 benchmark_conf would carry).  A request whose query fails the way the reference's graph fails (TopKV2 n < k ...)
 gets HTTP 400 with the op's message, as TF-Serving reports an InvalidArgument status.
@@ -154,6 +156,83 @@ def create_app(backend, user_floats, model_name="nann", max_batch_size=256, batc
     return app
 
 
+# ------------------------------------------------------------------------------------------------
+# gRPC: tensorflow.serving.PredictionService/Predict (the call of the reference's smoke test, README.md:200-221)
+# ------------------------------------------------------------------------------------------------
+# Messages are handled at the protobuf wire level (no tensorflow / tensorflow-serving-api packages here):
+#   PredictRequest  { ModelSpec model_spec = 1; map<string, TensorProto> inputs = 2; repeated string output_filter = 3; }
+#   PredictResponse { map<string, TensorProto> outputs = 1; ModelSpec model_spec = 2; }
+#   ModelSpec       { string name = 1; google.protobuf.Int64Value version = 2; string signature_name = 3; }
+def parse_predict_request(data):
+    """-> (model name, signature name, {input name: ndarray})"""
+    from ._pbwire import fields, tensor
+    name, sig, inputs = "", "", {}
+    for f, wt, v in fields(memoryview(data)):
+        if f == 1 and wt == 2:
+            for f2, _, v2 in fields(v):
+                if f2 == 1:
+                    name = bytes(v2).decode()
+                elif f2 == 3:
+                    sig = bytes(v2).decode()
+        elif f == 2 and wt == 2:                     # map entry: key = 1, value = 2
+            key, val = None, None
+            for f2, _, v2 in fields(v):
+                if f2 == 1:
+                    key = bytes(v2).decode()
+                elif f2 == 2:
+                    val = tensor(v2)
+            if key is not None and val is not None:
+                inputs[key] = val
+    return name, sig, inputs
+
+
+def encode_predict_response(model_name, signature, outputs):
+    from ._pbwire import enc_ld, enc_tensor
+    msg = b"".join(enc_ld(1, enc_ld(1, k.encode()) + enc_ld(2, enc_tensor(v))) for k, v in outputs.items())
+    return msg + enc_ld(2, enc_ld(1, model_name.encode()) + enc_ld(3, signature.encode()))
+
+
+def create_grpc_server(backend, user_floats, address="[::]:8500", model_name="nann", max_batch_size=256,
+                       batch_timeout_us=200, max_workers=32):
+    """grpc.Server answering /tensorflow.serving.PredictionService/Predict for inputs `comm_seq` (half or float
+    [B, user_floats]) and `level_topn` (int32[6]) with output `top_k` (int64 [B, k]), through the same dynamic
+    batcher as the REST front-end.  Returns (server, bound port, batcher); call server.start()."""
+    from concurrent import futures
+    import grpc
+    batcher = DynamicBatcher(backend, max_batch_size, batch_timeout_us)
+
+    def predict(request, context):
+        try:
+            name, sig, inputs = parse_predict_request(request)
+        except Exception as e:
+            context.abort(grpc.StatusCode.INVALID_ARGUMENT, f"malformed PredictRequest: {e}")
+        if name != model_name:
+            context.abort(grpc.StatusCode.NOT_FOUND, f"Servable not found for request: Latest({name})")
+        if "comm_seq" not in inputs or "level_topn" not in inputs:
+            context.abort(grpc.StatusCode.INVALID_ARGUMENT, "input tensors comm_seq and level_topn are required")
+        try:
+            users = np.asarray(inputs["comm_seq"], np.float32).reshape(-1, user_floats)
+            topn = [int(t) for t in np.asarray(inputs["level_topn"]).reshape(-1)]
+            if len(topn) != 6:
+                raise ValueError("level_topn must have 6 entries")
+            p = batcher.submit(users, topn)
+        except Exception as e:
+            context.abort(grpc.StatusCode.INVALID_ARGUMENT, str(e))
+        if np.any(p.status != 0):
+            bad = int(np.flatnonzero(p.status != 0)[0])
+            context.abort(grpc.StatusCode.INVALID_ARGUMENT, f"query {bad} failed with status {int(p.status[bad])} "
+                                                            f"(TopKV2: input must have at least k columns)")
+        return encode_predict_response(model_name, sig or "serving_default", {"top_k": np.ascontiguousarray(p.ids, np.int64)})
+
+    handler = grpc.method_handlers_generic_handler(
+        "tensorflow.serving.PredictionService",
+        {"Predict": grpc.unary_unary_rpc_method_handler(predict)})       # no (de)serializers: raw bytes in and out
+    server = grpc.server(futures.ThreadPoolExecutor(max_workers=max_workers))
+    server.add_generic_rpc_handlers((handler,))
+    port = server.add_insecure_port(address)
+    return server, port, batcher
+
+
 def searcher_backend(searcher):
     """backend over nann_b200.Searcher (one in-flight call at a time: the batcher has a single worker)."""
     def run(users, topn):
@@ -174,13 +253,25 @@ def main():
     ap.add_argument("--precision", default="tensor", choices=["exact", "tensor"])
     ap.add_argument("--host", default="0.0.0.0")
     ap.add_argument("--port", type=int, default=8501)
+    ap.add_argument("--grpc-port", type=int, default=8500, help="0 = REST only")
     args = ap.parse_args()
     ix = nb.Index.load(args.embs_dir, args.index_dir)
     sc = nb.Scorer.mlp(*sw.mlp_weights(seed=3))      # seeded mlp2x512 weights (the bench scorer); see tf_import.py for frozen graphs
     if args.precision == "tensor":
         sc.set_precision(nb.SCORER_TENSOR)
     se = nb.Searcher(ix, sc, args.max_batch_size, [int(t) for t in args.max_level_topn.split(",")])
-    app = create_app(searcher_backend(se), sc.user_floats, max_batch_size=args.max_batch_size, batch_timeout_us=args.batch_timeout_us)
+    lock = threading.Lock()                         # one searcher, two front-ends: serialise the backend calls
+    backend = searcher_backend(se)
+
+    def locked(users, topn):
+        with lock:
+            return backend(users, topn)
+
+    if args.grpc_port:
+        server, _, _ = create_grpc_server(locked, sc.user_floats, f"{args.host}:{args.grpc_port}", max_batch_size=args.max_batch_size,
+                                          batch_timeout_us=args.batch_timeout_us)
+        server.start()
+    app = create_app(locked, sc.user_floats, max_batch_size=args.max_batch_size, batch_timeout_us=args.batch_timeout_us)
     uvicorn.run(app, host=args.host, port=args.port, log_level="warning")
 
 

@@ -11,100 +11,12 @@ accepted: the four BatchNorm variables as separate constants (plain `freeze_grap
 
     python -m nann_b200.tf_import frozen_graph.pb attention_blob.npy
 """
-import struct
 import sys
 
 import numpy as np
 
 from . import scorer_weights as sw
-
-_DT = {1: np.float32, 2: np.float64, 3: np.int32, 9: np.int64, 19: np.float16}   # tensorflow/core/framework/types.proto
-
-
-# ------------------------------------------------------------------------------------------------
-# protobuf wire format (only what GraphDef / NodeDef / AttrValue / TensorProto need)
-# ------------------------------------------------------------------------------------------------
-def _varint(buf, i):
-    x = shift = 0
-    while True:
-        b = buf[i]
-        i += 1
-        x |= (b & 0x7F) << shift
-        if not b & 0x80:
-            return x, i
-        shift += 7
-
-
-def _fields(buf):
-    """yield (field_number, wire_type, value) for one message; value = int (varint / fixed) or memoryview (bytes)."""
-    i, n = 0, len(buf)
-    while i < n:
-        key, i = _varint(buf, i)
-        f, wt = key >> 3, key & 7
-        if wt == 0:
-            v, i = _varint(buf, i)
-        elif wt == 1:
-            v = struct.unpack_from("<Q", buf, i)[0]
-            i += 8
-        elif wt == 2:
-            ln, i = _varint(buf, i)
-            v = buf[i:i + ln]
-            i += ln
-        elif wt == 5:
-            v = struct.unpack_from("<I", buf, i)[0]
-            i += 4
-        else:
-            raise ValueError(f"unsupported protobuf wire type {wt}")
-        yield f, wt, v
-
-
-def _packed_varints(v):
-    out, i = [], 0
-    while i < len(v):
-        x, i = _varint(v, i)
-        out.append(x)
-    return out
-
-
-def _tensor(buf):
-    """TensorProto -> ndarray (dtype 1, tensor_shape 2, tensor_content 4, half_val 13, float_val 5, double_val 6,
-    int_val 7, int64_val 10); a short *_val list is extended with its last element, as TensorFlow does."""
-    dtype, dims, content, vals = 1, [], None, []
-    for f, wt, v in _fields(buf):
-        if f == 1:
-            dtype = v
-        elif f == 2:
-            for f2, _, v2 in _fields(v):
-                if f2 == 2:                                   # Dim
-                    size = 0
-                    for f3, _, v3 in _fields(v2):
-                        if f3 == 1:
-                            size = v3 - (1 << 64) if v3 >> 63 else v3
-                    dims.append(size)
-        elif f == 4:
-            content = bytes(v)
-        elif f == 5:                                          # float_val (packed or single fixed32)
-            vals += list(np.frombuffer(bytes(v), "<f4")) if wt == 2 else [struct.unpack("<f", struct.pack("<I", v))[0]]
-        elif f == 6:
-            vals += list(np.frombuffer(bytes(v), "<f8")) if wt == 2 else [struct.unpack("<d", struct.pack("<Q", v))[0]]
-        elif f in (7, 10, 13):                                # int_val / int64_val / half_val (bit patterns)
-            vals += _packed_varints(v) if wt == 2 else [v]
-    if dtype not in _DT:
-        return None
-    np_t = _DT[dtype]
-    n = int(np.prod(dims)) if dims else 1
-    if content is not None and len(content):
-        a = np.frombuffer(content, np.dtype(np_t).newbyteorder("<"), count=n)
-    else:
-        if dtype == 19:
-            a = np.asarray(vals, np.uint16).view(np.float16)
-        else:
-            a = np.asarray(vals, np_t)
-        if a.size == 0:
-            a = np.zeros(n, np_t)
-        elif a.size < n:
-            a = np.concatenate([a, np.full(n - a.size, a[-1], np_t)])
-    return np.array(a, np_t).reshape(dims)
+from ._pbwire import fields as _fields, tensor as _tensor
 
 
 def read_graph_def_consts(path_or_bytes):

@@ -93,3 +93,45 @@ def test_serving_a_real_searcher(small_world):
         np.testing.assert_array_equal(np.asarray(r.json()["outputs"], np.int64), want["ids"])
         # a level_topn the searcher was not sized for is the caller's error
         assert c.post("/v1/models/nann:predict", json={"inputs": {"comm_seq": users.tolist(), "level_topn": [9999] * 6}}).status_code == 400
+
+
+def test_grpc_prediction_service_predict():
+    """The reference's smoke test (README.md:200-221) over the wire: a PredictRequest with comm_seq (half) and level_topn
+    (int32) built with the wire encoder, sent to /tensorflow.serving.PredictionService/Predict."""
+    grpc = pytest.importorskip("grpc")
+    from nann_b200 import _pbwire as w
+    calls = []
+    server, port, batcher = serve.create_grpc_server(fake_backend(calls), user_floats=4, address="127.0.0.1:0", max_batch_size=8,
+                                                     batch_timeout_us=0)
+    server.start()
+    try:
+        def request(model, comm_seq, topn):
+            spec = w.enc_ld(1, model.encode()) + w.enc_ld(3, b"serving_default")
+            entries = [("comm_seq", comm_seq), ("level_topn", topn)]
+            return w.enc_ld(1, spec) + b"".join(w.enc_ld(2, w.enc_ld(1, k.encode()) + w.enc_ld(2, w.enc_tensor(v))) for k, v in entries)
+
+        ch = grpc.insecure_channel(f"127.0.0.1:{port}")
+        predict = ch.unary_unary("/tensorflow.serving.PredictionService/Predict")
+        comm_seq = np.asarray([[0.003, 1, 0, 0], [0.007, 1, 0, 0]], np.float16)       # the reference feeds half
+        resp = predict(request("nann", comm_seq, np.asarray(T, np.int32)), timeout=10)
+        outs, spec_name = {}, None
+        for f, wt, v in w.fields(memoryview(resp)):
+            if f == 1:
+                kv = {f2: v2 for f2, _, v2 in w.fields(v)}
+                outs[bytes(kv[1]).decode()] = w.tensor(kv[2])
+            elif f == 2:
+                spec_name = bytes({f2: v2 for f2, _, v2 in w.fields(v)}[1]).decode()
+        assert spec_name == "nann" and set(outs) == {"top_k"}
+        top_k = outs["top_k"]
+        assert top_k.dtype == np.int64 and top_k.shape == (2, 200) and top_k[:, 0].tolist() == [3, 7]
+        assert calls[-1] == (2, tuple(T))
+        with pytest.raises(grpc.RpcError) as e:
+            predict(request("other", comm_seq, np.asarray(T, np.int32)), timeout=10)
+        assert e.value.code() == grpc.StatusCode.NOT_FOUND
+        with pytest.raises(grpc.RpcError) as e:
+            predict(request("nann", np.asarray([[0, -1, 0, 0]], np.float16), np.asarray(T, np.int32)), timeout=10)
+        assert e.value.code() == grpc.StatusCode.INVALID_ARGUMENT
+        ch.close()
+    finally:
+        server.stop(0)
+        batcher.close()
