@@ -118,6 +118,6 @@ def enc_ld(field, payload):
 
 def enc_tensor(a):
     """ndarray -> TensorProto bytes (dtype, tensor_shape, tensor_content)"""
-    a = np.ascontiguousarray(a)
+    a = np.asarray(a, order="C")                      # keeps 0-d arrays 0-d
     shape = b"".join(enc_ld(2, enc_key(1, 0) + enc_varint(int(d))) for d in a.shape)
     return enc_key(1, 0) + enc_varint(DT_OF[a.dtype]) + enc_ld(2, shape) + enc_ld(4, a.astype(a.dtype.newbyteorder("<")).tobytes())

@@ -9,7 +9,11 @@ the inference graph does (`gamma * rsqrt(moving_variance + 1e-3)`, `beta - movin
 accepted: the four BatchNorm variables as separate constants (plain `freeze_graph`) or already folded by the
 `fold_constants` transform into `bn/batchnorm/mul` and `bn/batchnorm/sub`.
 
+`read_checkpoint` does the same for a V2 training checkpoint (TensorBundle: `<prefix>.index` is a leveldb-format table of
+BundleEntryProto, the values live in `<prefix>.data-*`), so `main.py test` weights can be taken from `model_dir` directly.
+
     python -m nann_b200.tf_import frozen_graph.pb attention_blob.npy
+    python -m nann_b200.tf_import model_dir/model.ckpt-12345 attention_blob.npy
 """
 import sys
 
@@ -48,6 +52,104 @@ def read_graph_def_consts(path_or_bytes):
             if t is not None:
                 out[name] = t
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# TensorBundle checkpoints (tf.train.Saver V2: <prefix>.index + <prefix>.data-XXXXX-of-YYYYY)
+# ------------------------------------------------------------------------------------------------
+# The .index file is a leveldb-format table (tensorflow/core/lib/io/table*): blocks of prefix-compressed
+# (key, value) entries + a restart array, each followed by a 5-byte trailer (compression type, masked crc32c);
+# a 48-byte footer holds the handles (offset, size varints) of the metaindex and index blocks and the magic
+# 0xdb4775248b80fb57.  Keys are tensor names, values BundleEntryProto {dtype 1, shape 2, shard_id 3, offset 4,
+# size 5, crc32c 6, slices 7}; the key "" carries BundleHeaderProto {num_shards 1}.
+_TABLE_MAGIC = 0xdb4775248b80fb57
+
+
+def _block_entries(buf, offset, size):
+    from ._pbwire import varint
+    if buf[offset + size] != 0:
+        raise ValueError("compressed table blocks are not supported (checkpoint index files are written uncompressed)")
+    blk = memoryview(buf)[offset:offset + size]
+    n_restarts = int.from_bytes(blk[size - 4:size], "little")
+    end = size - 4 - 4 * n_restarts
+    i, key = 0, b""
+    while i < end:
+        shared, i = varint(blk, i)
+        non_shared, i = varint(blk, i)
+        vlen, i = varint(blk, i)
+        key = key[:shared] + bytes(blk[i:i + non_shared])
+        i += non_shared
+        yield key, blk[i:i + vlen]
+        i += vlen
+
+
+def read_checkpoint_index(prefix):
+    """-> (num_shards, {tensor name: dict(dtype, shape, shard_id, offset, size)}) from <prefix>.index"""
+    from ._pbwire import varint
+    buf = open(prefix + ".index", "rb").read()
+    if len(buf) < 48 or int.from_bytes(buf[-8:], "little") != _TABLE_MAGIC:
+        raise ValueError(f"{prefix}.index is not a TensorBundle index (bad table magic)")
+    foot = memoryview(buf)[-48:]
+    i = 0
+    _, i = varint(foot, i); _, i = varint(foot, i)             # metaindex handle
+    ix_off, i = varint(foot, i); ix_size, i = varint(foot, i)
+    entries, num_shards = {}, 1
+    for _, handle in _block_entries(buf, ix_off, ix_size):     # index block: one entry per data block
+        d_off, j = varint(handle, 0)
+        d_size, j = varint(handle, j)
+        for key, val in _block_entries(buf, d_off, d_size):
+            if key == b"":
+                for f, _, v in _fields(val):
+                    if f == 1:
+                        num_shards = v
+                continue
+            e = dict(dtype=1, shape=[], shard_id=0, offset=0, size=0, sliced=False)
+            for f, wt, v in _fields(val):
+                if f == 1:
+                    e["dtype"] = v
+                elif f == 2:
+                    for f2, _, v2 in _fields(v):
+                        if f2 == 2:
+                            e["shape"].append(next((v3 for f3, _, v3 in _fields(v2) if f3 == 1), 0))
+                elif f == 3:
+                    e["shard_id"] = v
+                elif f == 4:
+                    e["offset"] = v
+                elif f == 5:
+                    e["size"] = v
+                elif f == 7:
+                    e["sliced"] = True
+            entries[key.decode()] = e
+    return num_shards, entries
+
+
+def read_checkpoint(prefix, names=None):
+    """-> {variable name: ndarray} of a V2 checkpoint (e.g. tf.train.latest_checkpoint(model_dir)); numeric dtypes only.
+    `names`: optional predicate on the variable name."""
+    from ._pbwire import DT
+    num_shards, entries = read_checkpoint_index(prefix)
+    out, files = {}, {}
+    for name, e in entries.items():
+        if (names is not None and not names(name)) or e["dtype"] not in DT:
+            continue
+        if e["sliced"]:
+            raise NotImplementedError(f"{name}: partitioned variables (tensor slices) are not supported")
+        sid = e["shard_id"]
+        if sid not in files:
+            files[sid] = np.memmap(f"{prefix}.data-{sid:05d}-of-{num_shards:05d}", np.uint8, "r")
+        raw = files[sid][e["offset"]:e["offset"] + e["size"]]
+        dt = np.dtype(DT[e["dtype"]]).newbyteorder("<")
+        n = int(np.prod(e["shape"])) if e["shape"] else 1
+        if raw.size != n * dt.itemsize:
+            raise ValueError(f"{name}: {raw.size} bytes in the data file, shape {e['shape']} needs {n * dt.itemsize}")
+        out[name] = np.frombuffer(bytes(raw), dt).astype(DT[e["dtype"]]).reshape(e["shape"])
+    return out
+
+
+def attention_blob_from_checkpoint(prefix):
+    """the variables of Model.forward straight from a training checkpoint (optimizer slots are ignored)"""
+    keep = lambda n: "Adam" not in n and "Momentum" not in n
+    return attention_blob_from_consts(read_checkpoint(prefix, keep))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -94,10 +196,11 @@ def attention_blob_from_frozen_graph(path):
 
 
 def main(argv=None):
+    import os
     argv = sys.argv[1:] if argv is None else argv
     if len(argv) != 2:
         raise SystemExit(__doc__)
-    blob = attention_blob_from_frozen_graph(argv[0])
+    blob = attention_blob_from_checkpoint(argv[0]) if os.path.exists(argv[0] + ".index") else attention_blob_from_frozen_graph(argv[0])
     np.save(argv[1], blob)
     print(f"{argv[1]}: {blob.size} floats")
 

@@ -140,3 +140,74 @@ def test_imported_blob_scores_like_the_oracle(oracle):
     table = (rng.standard_normal((500, 64)) / 8).astype(np.float32)
     ids = rng.integers(0, 500, 200).astype(np.int32)
     assert np.abs(nb.score_ids(s, user, table, ids) - a.score(user, table, ids)).max() <= 1e-5
+
+
+def _write_checkpoint(prefix, tensors, block_size=6):
+    """A V2 checkpoint written by hand: data file + leveldb-format index table (several data blocks, prefix-compressed
+    keys with a restart point every 2 entries, 5-byte block trailers, 48-byte footer)."""
+    from nann_b200._pbwire import enc_varint, enc_key, enc_ld, DT_OF
+    data, entries = bytearray(), [(b"", enc_key(1, 0) + enc_varint(1) + enc_ld(3, enc_key(1, 0) + enc_varint(1)))]   # header: num_shards 1
+    for name in sorted(tensors):
+        a = np.asarray(tensors[name], order="C")          # (ascontiguousarray would turn a scalar into shape (1,))
+        raw = a.astype(a.dtype.newbyteorder("<")).tobytes()
+        shape = b"".join(enc_ld(2, enc_key(1, 0) + enc_varint(int(d))) for d in a.shape)
+        e = enc_key(1, 0) + enc_varint(DT_OF[a.dtype]) + enc_ld(2, shape) + enc_key(4, 0) + enc_varint(len(data)) + \
+            enc_key(5, 0) + enc_varint(len(raw)) + enc_key(6, 5) + b"\0\0\0\0"
+        entries.append((name.encode(), e))
+        data += raw
+    open(prefix + ".data-00000-of-00001", "wb").write(bytes(data))
+
+    def block(items):
+        out, restarts, prev = bytearray(), [], b""
+        for i, (k, v) in enumerate(items):
+            shared = 0
+            if i % 2 == 0:
+                restarts.append(len(out))
+            else:
+                while shared < min(len(prev), len(k)) and prev[shared] == k[shared]:
+                    shared += 1
+            out += enc_varint(shared) + enc_varint(len(k) - shared) + enc_varint(len(v)) + k[shared:] + v
+            prev = k
+        for r in restarts or [0]:
+            out += struct.pack("<I", r)
+        out += struct.pack("<I", max(len(restarts), 1))
+        return bytes(out)
+
+    f, index_items = bytearray(), []
+    for b0 in range(0, len(entries), block_size):
+        items = entries[b0:b0 + block_size]
+        blk = block(items)
+        index_items.append((items[-1][0], enc_varint(len(f)) + enc_varint(len(blk))))
+        f += blk + b"\0" + b"\0\0\0\0"                     # trailer: no compression + (unchecked) crc
+    meta = block([])
+    meta_handle = enc_varint(len(f)) + enc_varint(len(meta))
+    f += meta + b"\0" + b"\0\0\0\0"
+    ix = block(index_items)
+    ix_handle = enc_varint(len(f)) + enc_varint(len(ix))
+    f += ix + b"\0" + b"\0\0\0\0"
+    foot = meta_handle + ix_handle
+    f += foot + b"\0" * (40 - len(foot)) + struct.pack("<Q", 0xdb4775248b80fb57)
+    open(prefix + ".index", "wb").write(bytes(f))
+
+
+def test_checkpoint_round_trip(tmp_path):
+    rng = np.random.default_rng(3)
+    c = _model_consts(rng, prefix="")
+    extra = {"global_step": np.asarray(12345, np.int64), "1_dnn/fc/kernel/Adam": np.zeros((128, 128), np.float32),
+             "1_dnn/fc/kernel/Adam_1": np.ones((128, 128), np.float32), "beta1_power": np.asarray(0.9, np.float32)}
+    prefix = str(tmp_path / "model.ckpt-12345")
+    _write_checkpoint(prefix, {**c, **extra})
+    shards, entries = tfi.read_checkpoint_index(prefix)
+    assert shards == 1 and set(entries) == set(c) | set(extra)
+    got = tfi.read_checkpoint(prefix)
+    for k, v in {**c, **extra}.items():
+        np.testing.assert_array_equal(got[k], v)
+        assert got[k].dtype == v.dtype and got[k].shape == v.shape
+    blob = tfi.attention_blob_from_checkpoint(prefix)
+    np.testing.assert_array_equal(blob.view(np.uint32), _expected_blob(c).view(np.uint32))
+    out = tmp_path / "blob.npy"
+    tfi.main([prefix, str(out)])                           # the CLI recognises a checkpoint prefix by its .index file
+    np.testing.assert_array_equal(np.load(out), blob)
+    (tmp_path / "bad.index").write_bytes(b"x" * 64)
+    with pytest.raises(ValueError):
+        tfi.read_checkpoint_index(str(tmp_path / "bad"))
