@@ -117,3 +117,31 @@ def test_npy_loader_host_side(tmp_path, oracle):
     with open(str(tmp_path / "v2.npy"), "wb") as f:
         np.lib.format.write_array(f, a, version=(2, 0))
     np.testing.assert_array_equal(nann_b200.huge_const(str(tmp_path / "v2.npy"), np.int64, (3, 4), device=-1).numpy(), a)
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/nann_b200.h compiles as strict C99 (no C++ or torch types in the ABI) and a C program links against
+    the library; without a GPU a compute entry point answers FAILED_PRECONDITION instead of falling back."""
+    from nann_b200 import build
+    so = build.build()
+    src = tmp_path / "abi.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include "nann_b200.h"
+int main(void) {
+  float in[4] = {1.f, 3.f, 2.f, 0.f}, val[2];
+  int32_t idx[2];
+  nann_status st;
+  if (nann_abi_version() != 1) return 2;
+  st = nann_topk_v2_f32(in, 1, 4, 2, 1, val, idx, NULL);
+  printf("%d %s\n", (int)st, st == NANN_OK ? "ok" : nann_last_error());
+  if (st == NANN_OK) return (idx[0] == 1 && idx[1] == 2) ? 0 : 3;
+  return st == NANN_FAILED_PRECONDITION ? 0 : 4;
+}
+''')
+    exe = tmp_path / "abi"
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                        str(src), "-o", str(exe), so, "-Wl,-rpath," + os.path.dirname(so)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
