@@ -26,8 +26,8 @@
  *     implementation behind this ABI: without a CUDA device every compute entry point fails with
  *     NANN_FAILED_PRECONDITION.
  *   - Streams: `stream` is a cudaStream_t passed as void* (NULL = default stream).  Calls that
- *     hand results back to host memory synchronise that stream before returning; calls whose
- *     outputs are device pointers are asynchronous.
+ *     hand results back to host memory synchronise that stream before returning; nann_search_batch and
+ *     nann_search_sharded with all-device outputs (and no host-side stats) only enqueue work.
  *   - Data-dependent output sizes (GroupGather, BitmapRefDifference) use an allocator callback,
  *     the C equivalent of OpKernelContext::allocate_output: the library calls
  *     alloc(ctx, output_index, n_elems) once per output and writes n_elems elements there.
@@ -299,6 +299,39 @@ nann_status nann_debug_tc_trace(long long* device_buffer_64x48);
  * ---------------------------------------------------------------------------------------- */
 nann_status nann_merge_topk(const float* scores, const int64_t* ids, int G, int B, int k_in,
                             int k_out, float* out_scores, int64_t* out_ids, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Sharded search: the corpus is row-sharded over `world` ranks (one per GPU), each with its own
+ * index + searcher; every query visits every shard and the per-shard top-k are exchanged and merged.  The
+ * exchange is part of the library: every rank owns a receive window in its HBM, maps the peers' windows
+ * (CUDA IPC across processes -- export / connect -- or nann_shard_group_connect_local for several members in
+ * one process) and the final top-k kernel of nann_search_sharded stores its (score, item id) records straight
+ * into every rank's window over NVLink; a merge kernel on the group's own stream then produces the global
+ * top k_out (order as nann_merge_topk: score descending, ties -> lower shard, then lower per-shard rank).
+ * Every rank must make the same sequence of nann_search_sharded calls (same B, level_topn_shard, k_out): it is
+ * a collective.  A query that failed on any shard fails as a whole (status of the first failing shard; ids -1).
+ * Outputs [B][k_out] / [B]:
+ *   - host pointers: the call returns when the merged results are in them;
+ *   - device pointers: the call only enqueues work (searches on `stream`, exchange + merge on the group's
+ *     stream, so that the next call's search overlaps them).  The outputs are complete once work ordered by
+ *     nann_shard_group_wait has run; give consecutive calls different output buffers.
+ * nann_shard_group_wait: host_block != 0 blocks the host until every merge issued so far has finished
+ * (DeadlineExceeded if a peer never delivered); otherwise makes `stream` wait for them.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct nann_shard_group nann_shard_group_t;
+nann_status nann_shard_group_create(int device, int rank, int world, int max_batch, int max_k_shard,
+                                    nann_shard_group_t** out);
+int nann_shard_group_handle_bytes(void);  /* 64: size of the opaque window handle (cudaIpcMemHandle_t) */
+nann_status nann_shard_group_export(nann_shard_group_t* g, void* handle);
+/* handles: [world][nann_shard_group_handle_bytes()] in rank order (exchanged out of band, e.g. an
+ * all-gather over torch.distributed / MPI); the own entry is ignored */
+nann_status nann_shard_group_connect(nann_shard_group_t* g, const void* handles);
+nann_status nann_shard_group_connect_local(nann_shard_group_t* const* members, int world);
+void nann_shard_group_destroy(nann_shard_group_t* g);
+nann_status nann_search_sharded(nann_searcher_t* s, nann_shard_group_t* g, const float* users, int B,
+                                const int32_t level_topn_shard[6], int k_out, int64_t* out_item_ids,
+                                float* out_scores, int32_t* out_status, void* stream);
+nann_status nann_shard_group_wait(nann_shard_group_t* g, void* stream, int host_block);
 
 /* ------------------------------------------------------------------------------------------
  * Executor: blaze-benchmark's load generator + session pool around the search call

@@ -97,6 +97,14 @@ def lib():
     L.nann_searcher_set_profile.argtypes = [vp, i32]
     L.nann_searcher_get_profile.argtypes = [vp, vp, vp, vp, vp]
     L.nann_merge_topk.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp]
+    L.nann_shard_group_create.argtypes = [i32, i32, i32, i32, i32, vp]
+    L.nann_shard_group_export.argtypes = [vp, vp]
+    L.nann_shard_group_connect.argtypes = [vp, vp]
+    L.nann_shard_group_connect_local.argtypes = [vp, i32]
+    L.nann_shard_group_destroy.restype = None
+    L.nann_shard_group_destroy.argtypes = [vp]
+    L.nann_search_sharded.argtypes = [vp, vp, vp, i32, vp, i32, vp, vp, vp, vp]
+    L.nann_shard_group_wait.argtypes = [vp, vp, i32]
     L.nann_eval_searcher_create.argtypes = [vp, vp, i32, vp, i32, vp]
     L.nann_eval_searcher_destroy.restype = None
     L.nann_eval_searcher_destroy.argtypes = [vp]

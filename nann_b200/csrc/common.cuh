@@ -38,12 +38,25 @@ nann_status fail(nann_status code, const char* fmt, ...);
     if (_s != NANN_OK) return _s;         \
   } while (0)
 
-// every kernel launch in the library goes through this so nann_kernel_launch_count() is exact
-#define NANN_LAUNCH(kernel, grid, block, smem, stream, ...)                 \
-  do {                                                                      \
-    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);             \
-    ::nann::g_launches.fetch_add(1, std::memory_order_relaxed);             \
+// every kernel launch in the library goes through this so nann_kernel_launch_count() is exact.  Launch-time
+// failures (no sm_100a image for the device, a bad shared-memory or cluster configuration) are NOT sticky and a
+// later cudaStreamSynchronize does not report them, so the launch result is checked right here.
+#define NANN_LAUNCH_OR(on_error, kernel, grid, block, smem, stream, ...)                                  \
+  do {                                                                                                    \
+    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                                           \
+    ::nann::g_launches.fetch_add(1, std::memory_order_relaxed);                                           \
+    cudaError_t _le = cudaPeekAtLastError();                                                              \
+    if (_le != cudaSuccess) {                                                                             \
+      cudaGetLastError();                                                                                 \
+      return on_error(::nann::fail(_le == cudaErrorNoKernelImageForDevice ? NANN_FAILED_PRECONDITION      \
+                                                                          : NANN_INTERNAL,                \
+                                   "launch of %s failed: %s (%s:%d)", #kernel, cudaGetErrorString(_le),    \
+                                   __FILE__, __LINE__));                                                  \
+    }                                                                                                     \
   } while (0)
+#define NANN_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  NANN_LAUNCH_OR(::nann::status_identity, kernel, grid, block, smem, stream, __VA_ARGS__)
+static inline nann_status status_identity(nann_status s) { return s; }
 
 nann_status require_device();  // NANN_FAILED_PRECONDITION when no CUDA device is usable
 bool is_device_ptr(const void* p);

@@ -34,6 +34,19 @@ nann_status require_device() {
                 "libnann_b200 needs a CUDA device (sm_100a); there is no CPU fallback (%s)",
                 e != cudaSuccess ? cudaGetErrorString(e) : "0 devices");
   }
+  // the library carries sm_100a code only: on any other GPU every launch would fail with "no kernel image"
+  static std::atomic<int> cc_ok[64];   // per device: 0 unknown, 1 ok, 2 wrong architecture
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return fail(NANN_FAILED_PRECONDITION, "no current CUDA device"); }
+  int state = cc_ok[dev & 63].load(std::memory_order_relaxed);
+  if (state == 0) {
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) { cudaGetLastError(); major = 0; }
+    state = major == 10 ? 1 : 2;
+    cc_ok[dev & 63].store(state, std::memory_order_relaxed);
+  }
+  if (state != 1)
+    return fail(NANN_FAILED_PRECONDITION, "libnann_b200 is built for sm_100a (B200) only; device %d has another architecture", dev);
   return NANN_OK;
 }
 

@@ -507,21 +507,17 @@ nann_status nann_searcher_set_trace(nann_searcher_t* s, int enable) {
   return NANN_OK;
 }
 
-nann_status nann_search_batch(nann_searcher_t* s, const float* users, int B, const int32_t T[6],
-                              int64_t* out_item_ids, float* out_scores, int32_t* out_status,
-                              nann_search_stats_t* stats, void* stream) {
-  NANN_TRY(require_device());
-  if (!s || !users || !T) return fail(NANN_INVALID_ARGUMENT, "nann_search_batch: null argument");
-  if (B < 0 || B > s->max_batch) return fail(NANN_INVALID_ARGUMENT, "batch %d outside [0, %d]", B, s->max_batch);
-  for (int i = 0; i < 6; ++i) {
-    if (T[i] < 0) return fail(NANN_INVALID_ARGUMENT, "Need k >= 0, got %d", T[i]);  // topk_op.cc:60-61
-    if (T[i] > s->maxT[i]) return fail(NANN_INVALID_ARGUMENT, "level_topn[%d]=%d exceeds the searcher's maximum %d", i, T[i], s->maxT[i]);
-  }
-  if (stats) memset(stats, 0, sizeof(*stats));
-  if (B == 0) return NANN_OK;
+}  // extern "C"
+
+namespace nann {
+
+// Enqueues the whole dataflow for B queries on `st` and returns without synchronising: per-shard results end up in
+// the searcher's out_sc / out_nodes / out_item ([B][max(k,1)]), per-query status and the per-round counters in
+// s->status / s->round_n / s->round_exp.  `push` (optional) makes the final top-k deliver its records to the shard
+// group's windows as well (lib_shard.inl).
+static nann_status search_enqueue(nann_searcher* s, const float* users, int B, const int32_t T[6], cudaStream_t st,
+                                  const ShardPush* push) {
   const nann_index* ix = s->ix;
-  cudaStream_t st = (cudaStream_t)stream;
-  NANN_CUDA(cudaSetDevice(ix->device));
   const int uf = nann_scorer_user_floats(s->sc);
   const int64_t mb = s->max_batch;
   const int k = T[5];
@@ -663,40 +659,80 @@ nann_status nann_search_batch(nann_searcher_t* s, const float* users, int B, con
     a.k = k; a.out_sc = s->out_sc; a.out_ids = s->out_nodes; a.out_stride = std::max(k, 1);
     a.item_ids = ix->item_ids; a.out_item_ids = s->out_item; a.out_item_stride = std::max(k, 1);
     a.status = s->status;
+    if (push) a.push = *push;
     NANN_TRY(topk_timed(a));
   }
-  // ---- results back
+  s->last_B = B; s->last_k = k;
+  return NANN_OK;
+}
+
+// after a stream synchronisation: fold the stage events of the last enqueue into the profile
+static void search_collect_profile(nann_searcher* s, int B) {
+  if (!s->profile) return;
+  const int64_t mb = s->max_batch;
+  for (int i = 0; i < s->ev_used; i += 2) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, s->ev[i], s->ev[i + 1]) == cudaSuccess) {
+      s->stage_ms[s->ev_stage[i / 2]] += ms;
+      s->stage_launches[s->ev_stage[i / 2]] += 1;
+    }
+  }
+  s->prof_calls += 1;
+  s->prof_rows += (int64_t)B * s->ix->n_ep;
+  for (int q = 0; q < B; ++q)
+    for (int r = 1; r < 5; ++r) s->prof_rows += s->h_round_n[(size_t)r * mb + q];
+}
+
+static nann_status search_check_args(nann_searcher* s, const float* users, int B, const int32_t T[6]) {
+  if (!s || !users || !T) return fail(NANN_INVALID_ARGUMENT, "nann_search_batch: null argument");
+  if (B < 0 || B > s->max_batch) return fail(NANN_INVALID_ARGUMENT, "batch %d outside [0, %d]", B, s->max_batch);
+  for (int i = 0; i < 6; ++i) {
+    if (T[i] < 0) return fail(NANN_INVALID_ARGUMENT, "Need k >= 0, got %d", T[i]);  // topk_op.cc:60-61
+    if (T[i] > s->maxT[i]) return fail(NANN_INVALID_ARGUMENT, "level_topn[%d]=%d exceeds the searcher's maximum %d", i, T[i], s->maxT[i]);
+  }
+  return NANN_OK;
+}
+
+}  // namespace nann
+
+extern "C" {
+
+nann_status nann_search_batch(nann_searcher_t* s, const float* users, int B, const int32_t T[6],
+                              int64_t* out_item_ids, float* out_scores, int32_t* out_status,
+                              nann_search_stats_t* stats, void* stream) {
+  NANN_TRY(require_device());
+  NANN_TRY(search_check_args(s, users, B, T));
+  if (stats) memset(stats, 0, sizeof(*stats));
+  if (B == 0) return NANN_OK;
+  const nann_index* ix = s->ix;
+  cudaStream_t st = (cudaStream_t)stream;
+  NANN_CUDA(cudaSetDevice(ix->device));
+  const int64_t mb = s->max_batch;
+  const int k = T[5];
+  NANN_TRY(search_enqueue(s, users, B, T, st, nullptr));
+
+  // ---- results back.  All-device outputs and nothing the host has to look at (stats, profile): asynchronous, the
+  // caller orders later work on `stream`; otherwise the call synchronises.
+  const bool dev_ids = !out_item_ids || is_device_ptr(out_item_ids), dev_sc = !out_scores || is_device_ptr(out_scores);
+  const bool dev_st = !out_status || is_device_ptr(out_status);
+  if (k > 0) {
+    if (out_item_ids)
+      NANN_CUDA(cudaMemcpyAsync(out_item_ids, s->out_item, (size_t)B * k * 8,
+                                dev_ids ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+    if (out_scores)
+      NANN_CUDA(cudaMemcpyAsync(out_scores, s->out_sc, (size_t)B * k * 4,
+                                dev_sc ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+  }
+  if (out_status && dev_st) NANN_CUDA(cudaMemcpyAsync(out_status, s->status, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
+  if (dev_ids && dev_sc && dev_st && !stats && !s->profile) return NANN_OK;
+
   s->h_round_n.resize((size_t)5 * mb); s->h_round_exp.resize((size_t)5 * mb); s->h_status.resize(B);
   NANN_CUDA(cudaMemcpyAsync(s->h_round_n.data(), s->round_n, (size_t)5 * mb * 4, cudaMemcpyDeviceToHost, st));
   NANN_CUDA(cudaMemcpyAsync(s->h_round_exp.data(), s->round_exp, (size_t)5 * mb * 4, cudaMemcpyDeviceToHost, st));
   NANN_CUDA(cudaMemcpyAsync(s->h_status.data(), s->status, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
-  if (k > 0) {
-    if (out_item_ids)
-      NANN_CUDA(cudaMemcpyAsync(out_item_ids, s->out_item, (size_t)B * k * 8,
-                                is_device_ptr(out_item_ids) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
-    if (out_scores)
-      NANN_CUDA(cudaMemcpyAsync(out_scores, s->out_sc, (size_t)B * k * 4,
-                                is_device_ptr(out_scores) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
-  }
   NANN_CUDA(cudaStreamSynchronize(st));
-  s->last_B = B; s->last_k = k;
-  if (s->profile) {
-    for (int i = 0; i < s->ev_used; i += 2) {
-      float ms = 0.f;
-      if (cudaEventElapsedTime(&ms, s->ev[i], s->ev[i + 1]) == cudaSuccess) {
-        s->stage_ms[s->ev_stage[i / 2]] += ms;
-        s->stage_launches[s->ev_stage[i / 2]] += 1;
-      }
-    }
-    s->prof_calls += 1;
-    s->prof_rows += (int64_t)B * ix->n_ep;
-    for (int q = 0; q < B; ++q)
-      for (int r = 1; r < 5; ++r) s->prof_rows += s->h_round_n[(size_t)r * mb + q];
-  }
-  if (out_status) {
-    if (is_device_ptr(out_status)) NANN_CUDA(cudaMemcpy(out_status, s->h_status.data(), (size_t)B * 4, cudaMemcpyHostToDevice));
-    else memcpy(out_status, s->h_status.data(), (size_t)B * 4);
-  }
+  search_collect_profile(s, B);
+  if (out_status && !dev_st) memcpy(out_status, s->h_status.data(), (size_t)B * 4);
   if (stats) {
     for (int q = 0; q < B; ++q) {
       if (s->h_status[q] != 0) stats->n_failed++;

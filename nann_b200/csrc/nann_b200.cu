@@ -17,5 +17,6 @@
 #include "lib_ops.inl"
 #include "lib_ragged.inl"
 #include "lib_search.inl"
+#include "lib_shard.inl"
 #include "lib_eval.inl"
 #include "lib_executor.inl"

@@ -415,6 +415,23 @@ __device__ __forceinline__ uint32_t order_key(float f) {
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
+// Shard exchange fused into the final top-k: the CTA that produced a query's per-shard top-k stores the
+// (score, item id) records and the query's status straight into EVERY rank's receive window -- peer HBM mapped
+// through CUDA IPC / peer access, i.e. plain st.global over NVLink -- and the last CTA to finish publishes
+// "shard `rank` has delivered sequence `seq`" in every window (release at system scope).
+constexpr int NANN_MAX_SHARDS = 16;
+struct ShardPush {
+  int world, rank, k, B;                            // world == 0: no exchange
+  float* sc[NANN_MAX_SHARDS];                       // window slot of peer p: scores [B][world][k]
+  int64_t* ids[NANN_MAX_SHARDS];                    //                        ids    [B][world][k]
+  int32_t* st[NANN_MAX_SHARDS];                     //                        status [B][world]
+  unsigned long long* arrive[NANN_MAX_SHARDS];      // peer p's flag "rank delivered seq" for this slot
+  const unsigned long long* my_done;                // own window: done[p] = 1 + last sequence rank p has merged
+  unsigned long long seq, need_done;                // slot is free once every done[p] >= need_done
+  unsigned int* counter;                            // local: CTAs finished (wraps to 0 at B)
+  int* error;                                       // local: set when a wait timed out (peer died / calls out of step)
+};
+
 struct TopkArgs {
   const float* a_sc; const int32_t* a_ids; int64_t a_stride; int a_n;        // fixed length
   const float* b_sc; int64_t b_sc_stride; const int32_t* b_ids; int64_t b_ids_stride;
@@ -430,7 +447,36 @@ struct TopkArgs {
   // eval traversal (model.py:255-271): list a has a per-row length, k is clamped to the row length, the
   // number of results per row is reported
   const int32_t* a_n_ptr; int clamp; int32_t* out_n;
+  ShardPush push;        // final top-k of a sharded search: results go to the peers' windows as well
 };
+
+// system-scope flag helpers of the shard exchange
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long shard_global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#ifndef NANN_SHARD_TIMEOUT_NS
+#define NANN_SHARD_TIMEOUT_NS 20000000000ull   // 20 s: a peer that never delivers must not hang the GPU
+#endif
+// spin until *flag >= want; false on timeout
+__device__ __forceinline__ bool shard_wait_flag(const unsigned long long* flag, unsigned long long want) {
+  if (ld_acquire_sys_u64(flag) >= want) return true;
+  const unsigned long long t0 = shard_global_ns();
+  for (;;) {
+    __nanosleep(200);
+    if (ld_acquire_sys_u64(flag) >= want) return true;
+    if (shard_global_ns() - t0 > NANN_SHARD_TIMEOUT_NS) return false;
+  }
+}
 
 constexpr int TOPK_THREADS = 512;
 constexpr int TOPK_MAX_K = 4096;
@@ -444,13 +490,10 @@ __device__ __forceinline__ uint32_t topk_key_at(const TopkArgs& a, int64_t row, 
   return a.ascending ? ~key : key;
 }
 
-__global__ void __launch_bounds__(TOPK_THREADS)
-topk_kernel(TopkArgs a) {
-  extern __shared__ unsigned long long sel[];  // [kpad] composite keys
+__device__ __forceinline__ void topk_row(const TopkArgs& a, const int64_t row, unsigned long long* sel) {
   __shared__ int hist[256];
   __shared__ uint32_t s_prefix;
   __shared__ int s_remaining, s_cnt, s_warp_cnt[TOPK_THREADS / 32], s_eq_taken;
-  const int64_t row = blockIdx.x;
   const int tid = threadIdx.x;
   if (a.status && a.status[row] != 0) return;
   const int b_n = a.b_row_off ? (int)(a.b_row_off[row + 1] - a.b_row_off[row])
@@ -582,6 +625,111 @@ topk_kernel(TopkArgs a) {
     if (a.out_ids) a.out_ids[o] = id;
     if (a.out_item_ids) a.out_item_ids[row * a.out_item_stride + r] = a.item_ids[id];
   }
+}
+
+__global__ void __launch_bounds__(TOPK_THREADS)
+topk_kernel(TopkArgs a) {
+  extern __shared__ unsigned long long sel[];  // [kpad] composite keys
+  const int64_t row = blockIdx.x;
+  topk_row(a, row, sel);
+  if (a.push.world == 0) return;
+  // ---- shard exchange epilogue: this query's records -> every rank's window, then the delivery flags
+  const ShardPush& P = a.push;
+  const int tid = threadIdx.x;
+  __shared__ int s_ok;
+  if (tid == 0) {            // the slot must have been merged by everyone `depth` sequences ago
+    bool ok = true;
+    for (int p = 0; p < P.world && ok; ++p) ok = shard_wait_flag(P.my_done + p, P.need_done);
+    if (!ok) *P.error = 1;
+    s_ok = ok ? 1 : 0;
+  }
+  __syncthreads();           // also orders the emit loop's writes before the re-reads below (same thread anyway)
+  if (s_ok) {
+    const int32_t st = a.status ? a.status[row] : 0;
+    for (int r = tid; r < P.k; r += TOPK_THREADS) {
+      const float sc = st == 0 ? a.out_sc[row * a.out_stride + a.out_offset + r] : __int_as_float(-1);
+      const int64_t id = st == 0 ? a.out_item_ids[row * a.out_item_stride + r] : (int64_t)-1;
+      const int64_t o = (row * P.world + P.rank) * P.k + r;
+      for (int p = 0; p < P.world; ++p) { P.sc[p][o] = sc; P.ids[p][o] = id; }
+    }
+    if (tid < P.world) P.st[tid][row * P.world + P.rank] = st;
+  }
+  __threadfence_system();    // every thread: its stores are ordered before the counter increment below
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned int prev = atomicInc(P.counter, (unsigned int)(P.B - 1));
+    if (prev == (unsigned int)(P.B - 1)) {   // last CTA: all B queries are in every window
+      __threadfence_system();
+      for (int p = 0; p < P.world; ++p) st_release_sys_u64(P.arrive[p], P.seq + 1);
+    }
+  }
+}
+
+// ---- shard merge: one CTA per query sorts the world*k_in records of its window row (stable: score desc, ties ->
+// lower shard, then lower per-shard rank == nann_merge_topk) and emits the best k_out; the last CTA tells every
+// peer that this rank is done with the slot.
+struct ShardMergeArgs {
+  int world, rank, k_in, k_out, B;
+  const float* sc; const int64_t* ids; const int32_t* st;       // own window slot
+  float* out_sc; int64_t* out_ids; int32_t* out_status;          // [B][k_out], [B]
+  unsigned long long* done[NANN_MAX_SHARDS];                    // peer p's done[rank]
+  unsigned long long seq;
+  unsigned int* counter;
+  const int* error;                                              // a wait timed out: every query fails
+};
+constexpr int SHARD_MERGE_THREADS = 256;
+__global__ void __launch_bounds__(SHARD_MERGE_THREADS)
+shard_merge_kernel(ShardMergeArgs a) {
+  extern __shared__ unsigned long long mkeys[];   // [npad]
+  const int64_t row = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int n = a.world * a.k_in;
+  int st = *a.error ? NANN_DEADLINE_EXCEEDED : 0;
+  for (int g = 0; g < a.world && st == 0; ++g) st = a.st[row * a.world + g];   // first failing shard decides
+  if (st != 0) {             // what a failed single-shard search leaves behind: ids -1, scores 0xFFFFFFFF
+    for (int r = tid; r < a.k_out; r += SHARD_MERGE_THREADS) {
+      a.out_sc[row * a.k_out + r] = __int_as_float(-1);
+      a.out_ids[row * a.k_out + r] = -1;
+    }
+  } else {
+    int npad = 1;
+    while (npad < n) npad <<= 1;
+    for (int i = tid; i < npad; i += SHARD_MERGE_THREADS)
+      mkeys[i] = i < n ? (((unsigned long long)(~order_key(a.sc[row * n + i])) << 32) | (uint32_t)i) : ~0ull;
+    __syncthreads();
+    for (int size = 2; size <= npad; size <<= 1) {
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        for (int t = tid; t < (npad >> 1); t += SHARD_MERGE_THREADS) {
+          const int lo = ((t / stride) * (stride << 1)) + (t % stride);
+          const int hi = lo + stride;
+          const bool up = ((lo & size) == 0);
+          const unsigned long long x = mkeys[lo], y = mkeys[hi];
+          if ((x > y) == up) { mkeys[lo] = y; mkeys[hi] = x; }
+        }
+        __syncthreads();
+      }
+    }
+    for (int r = tid; r < a.k_out; r += SHARD_MERGE_THREADS) {
+      const int pos = (int)(uint32_t)(mkeys[r] & 0xffffffffull);
+      a.out_sc[row * a.k_out + r] = a.sc[row * n + pos];
+      a.out_ids[row * a.k_out + r] = a.ids[row * n + pos];
+    }
+  }
+  if (tid == 0 && a.out_status) a.out_status[row] = st;
+  __syncthreads();           // all reads of the window row are done
+  if (tid == 0) {
+    __threadfence();
+    const unsigned int prev = atomicInc(a.counter, (unsigned int)(a.B - 1));
+    if (prev == (unsigned int)(a.B - 1)) {
+      __threadfence_system();
+      for (int p = 0; p < a.world; ++p) st_release_sys_u64(a.done[p], a.seq + 1);
+    }
+  }
+}
+// one warp: lane p waits for shard p's delivery of `seq` into this rank's window slot
+__global__ void shard_wait_kernel(const unsigned long long* arrive, int world, unsigned long long seq, int* error) {
+  const int p = threadIdx.x;
+  if (p < world && !shard_wait_flag(arrive + p, seq + 1)) *error = 1;
 }
 
 // ---- K6: G-way shard merge: rows of G*k_in (score,id) in allgather layout [G][B][k_in] ------

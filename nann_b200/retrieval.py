@@ -160,9 +160,15 @@ class Searcher:
         """All-device form: users, out_ids (i64 [B,k]) and out_scores (f32 [B,k]) are CUDA tensors;
         nothing but the per-query status/counters crosses PCIe.  Returns (status, stats dict)."""
         uf = self.scorer.user_floats
-        u = users.contiguous().reshape(-1, uf)
+        if not (ops._is_torch(users) and users.is_cuda):
+            raise TypeError("search_device: users must be a CUDA tensor (use search() for host arrays)")
+        u = users.contiguous().float().reshape(-1, uf)     # comm_seq arrives as fp16 in the reference's serving graph
         B = u.shape[0]
         T = (C.c_int32 * 6)(*[int(t) for t in level_topn])
+        k = max(int(level_topn[5]), 0)
+        for t, dt, name in ((out_ids, "int64", "out_ids"), (out_scores, "float32", "out_scores")):
+            if not (ops._is_torch(t) and t.is_cuda and t.is_contiguous() and str(t.dtype).endswith(dt) and tuple(t.shape) == (B, k)):
+                raise TypeError(f"search_device: {name} must be a contiguous CUDA {dt} tensor of shape ({B}, {k})")
         status = np.empty(B, np.int32)
         st = _lib.SearchStats()
         check(_lib.lib().nann_search_batch(self._h, C.c_void_p(u.data_ptr()), B, T, C.c_void_p(out_ids.data_ptr()),

@@ -44,8 +44,15 @@ def _worker(rank, world, port, out_dir):
     users = nix.synthetic_queries(full, B, seed=2)                     # identical on every rank
     r = oix.search_batch_mlp(orc.Mlp(*sw.mlp_weights()), users, Ts, nthreads=1)
     assert np.all(r["status"] == 0)
-    g_sc, g_id = nd.allgather_results(torch.from_numpy(r["scores"]), torch.from_numpy(r["ids"]))
-    assert tuple(g_sc.shape) == (world, B, Ts[5])
+    status = r["status"].copy()
+    if rank == 1:
+        status[2] = 3                                                   # pretend query 2 failed on shard 1 only
+    g_sc, g_id, g_st = nd.allgather_results(torch.from_numpy(r["scores"]), torch.from_numpy(r["ids"]), status)
+    assert tuple(g_sc.shape) == (world, B, Ts[5]) and tuple(g_st.shape) == (world, B)
+    comb = nd.combine_status(g_st.numpy())                              # every rank learns of the failure
+    assert comb[2] == 3 and np.all(np.delete(comb, 2) == 0)
+    m_sc2, m_id2 = nd.mask_failed(g_sc, g_id, g_st)
+    assert torch.all(m_id2[1, 2] == -1) and torch.all(torch.isinf(m_sc2[1, 2])) and torch.equal(m_id2[0], g_id[0])
     np.testing.assert_array_equal(g_sc[rank].numpy(), r["scores"])   # own slab sits at index `rank`
     m_sc, m_id = _numpy_merge(g_sc.numpy(), g_id.numpy(), T[5])
     np.save(os.path.join(out_dir, f"merged_{rank}.npy"), m_id)

@@ -344,3 +344,80 @@ def test_two_shards_on_one_device_merge_like_the_oracle(nb, oracle, world):
         o = np.argsort(-cs, kind="stable")[:T[5]]
         np.testing.assert_array_equal(m_id[q], ci[o])
         np.testing.assert_array_equal(m_sc[q].view(np.uint32), cs[o].view(np.uint32))
+
+
+def test_shard_group_exchange_in_library(nb, oracle, world):
+    """nann_search_sharded: two shard members in ONE process on one device (peer windows = plain device pointers).
+    The final top-k kernel pushes its records into both windows, the merge kernel runs on the group's stream; six
+    sequences exercise the double-buffered windows and the done-flag back-pressure.  The merged result equals the
+    stable merge (score desc, ties -> lower shard, then lower rank) of the per-shard ORACLE results, bit for bit."""
+    import torch
+    from nann_b200 import index as nix
+    from nann_b200.distributed import ShardGroup, shard_bounds, shard_level_topn
+    T = world["T"]
+    Ts = shard_level_topn(T, 2)
+    B, n_seq = 8, 6
+    shards, want = [], []
+    for r in range(2):
+        lo, hi = shard_bounds(world["emb"].shape[0], 2, r)
+        emb, ids = world["emb"][lo:hi], world["item_ids"][lo:hi]
+        g = nix.build_hnsw(emb, M=16, m_levels=6, seed=4 + r, n_cand=40, device="cpu")
+        ix = nb.Index.from_arrays(emb, ids, g["enter_points"], g["values"], g["row_splits"])
+        shards.append((ix, nb.Searcher(ix, world["scorer"], B, Ts)))
+        oix = oracle.Index(emb, ids, g["enter_points"].astype(np.int32), [v.astype(np.int32) for v in g["values"]], g["row_splits"])
+        want.append([oix.search_batch_mlp(world["omlp"], world["queries"][i * B:(i + 1) * B], Ts, nthreads=0) for i in range(n_seq)])
+    members = [ShardGroup(r, 2, B, Ts[5]) for r in range(2)]
+    ShardGroup.connect_local(members)
+    outs = [[(torch.empty((B, T[5]), dtype=torch.int64, device="cuda"), torch.empty((B, T[5]), dtype=torch.float32, device="cuda"),
+              torch.empty((B,), dtype=torch.int32, device="cuda")) for _ in range(n_seq)] for _ in range(2)]
+    before = nb.launch_count()
+    for i in range(n_seq):
+        users = torch.from_numpy(world["queries"][i * B:(i + 1) * B]).cuda()
+        for r in range(2):                      # both members enqueue on the same stream; nothing blocks the host
+            members[r].search(shards[r][1], users, Ts, T[5], *outs[r][i])
+    for m in members:
+        m.wait()
+    assert nb.launch_count() - before >= n_seq * 2 * 20
+    for i in range(n_seq):
+        for q in range(B):
+            cs = np.concatenate([want[0][i]["scores"][q], want[1][i]["scores"][q]])
+            ci = np.concatenate([want[0][i]["ids"][q], want[1][i]["ids"][q]])
+            o = np.argsort(-cs, kind="stable")[:T[5]]
+            for r in range(2):                  # every rank ends with the same global list
+                np.testing.assert_array_equal(outs[r][i][0][q].cpu().numpy(), ci[o])
+                np.testing.assert_array_equal(outs[r][i][1][q].cpu().numpy().view(np.uint32), cs[o].view(np.uint32))
+        assert all(int(outs[r][i][2].sum()) == 0 for r in range(2))
+
+
+def test_shard_group_failed_query_fails_everywhere(nb, oracle, world):
+    """A query whose search fails on ONE shard (TopKV2 n < k there) fails on every rank alike: combined status,
+    ids -1 -- never a half-merged list."""
+    import torch
+    from nann_b200 import index as nix
+    from nann_b200.distributed import ShardGroup, shard_bounds
+    B = 4
+    Ts = [[20, 40, 40, 40, 40, 40], [20, 40, 40, 40, 40, 40]]
+    users = torch.from_numpy(world["queries"][:B]).cuda()
+    members = [ShardGroup(r, 2, B, 40) for r in range(2)]
+    ShardGroup.connect_local(members)
+    searchers, keep = [], []
+    for r in range(2):
+        lo, hi = shard_bounds(world["emb"].shape[0], 2, r)
+        if r == 1:
+            hi = lo + 300                        # a tiny shard: level_topn[0]=20 > its enter points -> InvalidArgument
+        emb, ids = world["emb"][lo:hi], world["item_ids"][lo:hi]
+        g = nix.build_hnsw(emb, M=16, m_levels=6, seed=4 + r, n_cand=40, device="cpu")
+        if r == 1:
+            assert len(g["enter_points"]) < 20
+        ix = nb.Index.from_arrays(emb, ids, g["enter_points"], g["values"], g["row_splits"])
+        keep.append(ix)
+        searchers.append(nb.Searcher(ix, world["scorer"], B, Ts[r]))
+    outs = [(torch.zeros((B, 40), dtype=torch.int64, device="cuda"), torch.zeros((B, 40), dtype=torch.float32, device="cuda"),
+             torch.zeros((B,), dtype=torch.int32, device="cuda")) for _ in range(2)]
+    for r in range(2):
+        members[r].search(searchers[r], users, Ts[r], 40, *outs[r])
+    for m in members:
+        m.wait()
+    for r in range(2):
+        assert np.all(outs[r][2].cpu().numpy() == 3)
+        assert np.all(outs[r][0].cpu().numpy() == -1)
