@@ -8,12 +8,16 @@ visited-filter rounds, 6 top-k) on synthetic data.  Default workload = BASELINE 
 
   python bench.py --gpus 1 --steps 10 --warmup 3            # this repo's CUDA path
   python bench.py --impl reference ...                       # the reference algorithm on the host cores
-  torchrun --nproc-per-node N bench.py --gpus N ...          # N shards of --n-items rows, global batch N x --batch (weak scaling)
+  torchrun --nproc-per-node N bench.py --gpus N ...          # the SAME --n-items corpus row-sharded N ways,
+                                                             # global batch N x --batch, per-shard beams calibrated
+                                                             # so that recall@200 equals the one-GPU operating point
+  ... --n-items 100000000 --gpus 8                           # BASELINE configs[3]
 
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
 """
 import argparse
 import hashlib
+import importlib.util
 import json
 import os
 import statistics
@@ -32,10 +36,39 @@ EF_TOPN = {200: [100, 200, 200, 200, 200, 200],      # reference README.md:216
 MAC_PER_ROW = 256 * 512 + 512 * 512 + 512            # un-hoisted algorithmic count
 ROW_BYTES = 512
 CACHE = os.environ.get("NANN_BENCH_CACHE", "/tmp/nann_b200_bench_cache")
+BIG = 16_000_000                                     # corpora above this are generated block-wise
+N_BLOCKS = 64
+SCALES = (0.5, 0.625, 0.75, 0.875, 1.0, 1.125, 1.25, 1.5, 1.75, 2.0, 2.5, 3.0, 4.0)
+RECALL_TOL = 0.005
 
 
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
+
+
+def _by_path(name):
+    """nann_b200/<name>.py as a plain module, WITHOUT importing the package: the reference arm must not load
+    libnann_b200.so (these modules are numpy / torch only)."""
+    key = "_nann_helper_" + name
+    if key in sys.modules:
+        return sys.modules[key]
+    spec = importlib.util.spec_from_file_location(key, os.path.join(ROOT, "nann_b200", name + ".py"))
+    m = importlib.util.module_from_spec(spec)
+    sys.modules[key] = m
+    spec.loader.exec_module(m)
+    return m
+
+
+def nix():
+    return _by_path("index")
+
+
+def shard_bounds(n, world, rank):
+    return _by_path("distributed").shard_bounds(n, world, rank)
+
+
+def shard_topn(T, world, scale=1.0):
+    return _by_path("distributed").shard_level_topn(T, world, scale)
 
 
 def peaks():
@@ -48,65 +81,82 @@ def peaks():
 
 
 # ------------------------------------------------------------------------------------------------
-# workload: corpus shard + HNSW files (cached on local disk so both arms of a box reuse them)
+# workload: ONE corpus of --n-items rows whatever the number of GPUs; rank r of N searches rows [lo, hi)
 # ------------------------------------------------------------------------------------------------
-from nann_b200.distributed import shard_bounds, shard_level_topn as shard_topn  # noqa: E402
-
-
 def corpus_block(n_rows, block):
-    """rows and GLOBAL item ids of block `block` of the sharded corpus (N>1): the corpus is DEFINED as the
-    concatenation of per-rank blocks (seed 100+block), so no rank ever materialises more than its own block
-    (+ block 0, which the queries are drawn from)."""
-    from nann_b200 import index as nix
-    emb = nix.synthetic_corpus(n_rows, 128, seed=100 + block)
-    ids = np.int64(block) * n_rows + nix.synthetic_item_ids(n_rows, seed=200 + block)
+    """rows and GLOBAL item ids of block `block` of a block-wise defined corpus (seed 100+block)"""
+    emb = nix().synthetic_corpus(n_rows, 128, seed=100 + block)
+    ids = np.int64(block) * n_rows + nix().synthetic_item_ids(n_rows, seed=200 + block)
     return emb, ids
 
 
+def corpus_rows(n_items, lo, hi):
+    """rows [lo, hi) of the corpus and their item ids.  Up to 16M rows the corpus is one seeded draw (the same
+    arrays for every N, identical to the single-GPU configs); above, it is DEFINED as 64 seeded blocks so that
+    no rank ever materialises more than the blocks its rows touch."""
+    if n_items <= BIG:
+        full = nix().synthetic_corpus(n_items, 128, seed=0)
+        ids = nix().synthetic_item_ids(n_items, seed=1)
+        return np.ascontiguousarray(full[lo:hi]), np.ascontiguousarray(ids[lo:hi])
+    per = -(-n_items // N_BLOCKS)
+    embs, idl = [], []
+    for b in range(lo // per, (hi - 1) // per + 1):
+        b_lo, b_hi = b * per, min((b + 1) * per, n_items)
+        e, _ = corpus_block(b_hi - b_lo, b)
+        s0, s1 = max(lo, b_lo) - b_lo, min(hi, b_hi) - b_lo
+        embs.append(e[s0:s1])
+        idl.append(np.arange(b_lo + s0, b_lo + s1, dtype=np.int64) + 7_000_000_000)     # id != row
+    return np.ascontiguousarray(np.concatenate(embs)), np.concatenate(idl)
+
+
+def query_pool(n_items):
+    """the rows queries are drawn from (+ noise): the whole corpus, or block 0 of a block-wise corpus"""
+    if n_items <= BIG:
+        return nix().synthetic_corpus(n_items, 128, seed=0)
+    per = -(-n_items // N_BLOCKS)
+    return corpus_block(min(per, n_items), 0)[0]
+
+
+def builder_name(device):
+    """the hand-written CUDA builder of the library when a GPU is there (nann_b200/builder.py), the torch builder
+    otherwise (CPU: small test corpora only)"""
+    if str(device).startswith("cuda") and os.environ.get("NANN_BENCH_TORCH_BUILDER", "0") != "1" and \
+            os.path.exists(os.path.join(ROOT, "nann_b200", "builder.py")):
+        return "cuda-builder"
+    return "torch-builder"
+
+
+def build_graph(emb, seed, device):
+    if builder_name(device) == "cuda-builder":
+        from nann_b200 import builder
+        dev_index = int(str(device).split(":")[1]) if ":" in str(device) else 0
+        return builder.build_hnsw(emb, M=32, start_level=2, seed=seed, device=dev_index)
+    return nix().build_hnsw(emb, M=32, start_level=2, seed=seed, device=device)
+
+
+def shard_dir(n_items, world, rank):
+    key = hashlib.sha1(json.dumps([n_items, world, rank, 128, 32, 4, "r2"]).encode()).hexdigest()[:16]
+    return os.path.join(CACHE, f"shard_{n_items}_{world}_{rank}_{key}")
+
+
 def get_shard(n_items, world, rank, device):
-    """-> dict(emb, item_ids (GLOBAL ids), ep, values, row_splits) for this rank's rows.
-    world == 1: the whole n_items corpus (seed 0).  world > 1 (weak scaling): block `rank` of n_items rows."""
-    from nann_b200 import index as nix
-    if world > 1:
-        key = hashlib.sha1(json.dumps([n_items, "block", rank, 128, 32, 4, "w1"]).encode()).hexdigest()[:16]
-        root = os.path.join(CACHE, f"block_{n_items}_{rank}_{key}")
-        embs_dir, index_dir = os.path.join(root, "embeddings"), os.path.join(root, "index")
-        big = n_items > 4_000_000
-        if big or not os.path.exists(os.path.join(root, "done")):
-            t = time.time()
-            emb, ids = corpus_block(n_items, rank)
-            g = nix.build_hnsw(emb, M=32, start_level=2, seed=4 + rank, device=device)
-            log(f"[bench] rank {rank}: built HNSW over block {rank} ({n_items} rows) in {time.time() - t:.1f}s on {device}")
-            if big:
-                return dict(emb=emb, item_ids=ids, ep=g["enter_points"], values=g["values"], row_splits=g["row_splits"])
-            nix.save_index(embs_dir, index_dir, emb, ids, g)
-            open(os.path.join(root, "done"), "w").write("ok")
-        emb, item_ids, g = nix.load_index_arrays(embs_dir, index_dir)
-        return dict(emb=emb, item_ids=item_ids, ep=g["enter_points"], values=g["values"], row_splits=g["row_splits"])
-    key = hashlib.sha1(json.dumps([n_items, world, rank, 128, 32, 4, "v3"]).encode()).hexdigest()[:16]
-    root = os.path.join(CACHE, f"shard_{n_items}_{world}_{rank}_{key}")
-    embs_dir, index_dir = os.path.join(root, "embeddings"), os.path.join(root, "index")
+    """-> dict(emb, item_ids (GLOBAL ids), ep, values, row_splits) for rows [lo, hi) of the corpus."""
     lo, hi = shard_bounds(n_items, world, rank)
-    if hi - lo > 4_000_000:      # big shards (configs[2], configs[3]): ~10 GB of files per shard -- keep them in memory
+    root = shard_dir(n_items, world, rank)
+    embs_dir, index_dir = os.path.join(root, "embeddings"), os.path.join(root, "index")
+    big = hi - lo > 4_000_000        # ~10 GB of files per shard: keep them in memory
+    if big or not os.path.exists(os.path.join(root, "done")):
         t = time.time()
-        emb = np.ascontiguousarray(nix.synthetic_corpus(n_items, 128, seed=0)[lo:hi])
-        ids = nix.synthetic_item_ids(n_items, seed=1)[lo:hi]
-        g = nix.build_hnsw(emb, M=32, start_level=2, seed=4 + rank, device=device)
-        log(f"[bench] rank {rank}: built HNSW over rows [{lo},{hi}) in {time.time() - t:.1f}s on {device} (partitioned candidate search)")
-        return dict(emb=emb, item_ids=ids, ep=g["enter_points"], values=g["values"], row_splits=g["row_splits"],
-                    embs_dir=None, index_dir=None)
-    if not os.path.exists(os.path.join(root, "done")):
-        t = time.time()
-        full = nix.synthetic_corpus(n_items, 128, seed=0)
-        ids = nix.synthetic_item_ids(n_items, seed=1)
-        emb = np.ascontiguousarray(full[lo:hi])
-        g = nix.build_hnsw(emb, M=32, start_level=2, seed=4 + rank, device=device)
-        nix.save_index(embs_dir, index_dir, emb, ids[lo:hi], g)
+        emb, ids = corpus_rows(n_items, lo, hi)
+        t1 = time.time()
+        g = build_graph(emb, 4 + rank, device)
+        log(f"[bench] rank {rank}: rows [{lo},{hi}) generated in {t1 - t:.1f}s, HNSW built in {time.time() - t1:.1f}s ({builder_name(device)}, {device})")
+        if big:
+            return dict(emb=emb, item_ids=ids, ep=g["enter_points"], values=g["values"], row_splits=g["row_splits"])
+        nix().save_index(embs_dir, index_dir, emb, ids, g)
         open(os.path.join(root, "done"), "w").write("ok")
-        log(f"[bench] rank {rank}: built HNSW over rows [{lo},{hi}) in {time.time() - t:.1f}s on {device}")
-    emb, item_ids, g = nix.load_index_arrays(embs_dir, index_dir)
-    return dict(emb=emb, item_ids=item_ids, ep=g["enter_points"], values=g["values"], row_splits=g["row_splits"],
-                embs_dir=embs_dir, index_dir=index_dir)
+    emb, item_ids, g = nix().load_index_arrays(embs_dir, index_dir)
+    return dict(emb=emb, item_ids=item_ids, ep=g["enter_points"], values=g["values"], row_splits=g["row_splits"])
 
 
 class ClockSampler:
@@ -168,22 +218,62 @@ class ClockSampler:
                 "scope": getattr(self, "scope", "sampler lifetime")}
 
 
+def nvlink_tx_rx_kib(gpu_index):
+    """sum over the links of GPU `gpu_index` of the NVLink data counters (KiB), or None"""
+    try:
+        r = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(gpu_index)], capture_output=True, text=True, timeout=10)
+        tx = rx = 0
+        seen = False
+        for line in r.stdout.splitlines():
+            parts = line.replace(":", " ").split()
+            if "Tx" in parts and "KiB" in parts:
+                tx += int(parts[parts.index("KiB") - 1]); seen = True
+            if "Rx" in parts and "KiB" in parts:
+                rx += int(parts[parts.index("KiB") - 1]); seen = True
+        return (tx, rx) if seen else None
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------------------------------
+def workload_config(args, T, world):
+    which = {(1_000_000, 256, 200): "BASELINE configs[1]", (10_000_000, 1024, 400): "BASELINE configs[2]"}.get(
+        (args.n_items, args.batch, args.ef), "BASELINE configs[4] sweep point" if args.n_items == 1_000_000 else "custom")
+    l2 = "inputs larger than L2: 512 MB embedding table + 260 MB graph per 1M rows, fresh queries every step"
+    if world > 1:
+        shape = "BASELINE configs[3]" if args.n_items == 100_000_000 and world == 8 else f"BASELINE configs[3] shape on the {which} corpus"
+        return {"workload": f"{args.n_items} items d=128 f32 row-sharded over {world} GPUs ({-(-args.n_items // world)} rows + their own HNSW each), "
+                            f"global batch={args.batch * world} queries ({args.batch} per GPU), scoring MLP 2x512, ef_search={args.ef}, HNSW M=32 ({shape})",
+                "level_topn": list(T),
+                "parallelism": f"corpus row-sharded x{world}: every query visits every shard; per-shard top-k pushed into every rank's window over "
+                               f"NVLink by the final top-k kernel, merge kernel per rank (nann_search_sharded); batch grows with N (weak scaling)",
+                "l2": l2}
+    return {"workload": f"{args.n_items} items d=128 f32, batch={args.batch} queries, scoring MLP 2x512, "
+                        f"ef_search={args.ef}, HNSW M=32 ({which})",
+            "level_topn": list(T), "parallelism": "1 GPU", "l2": l2}
+
+
 def run_reference(args, T, rank, world):
-    """The reference algorithm (CPU custom-op path restated in oracle/) on the host cores:
-    batch=1 per request, one in-flight request per core (blaze-benchmark consumers)."""
+    """The reference algorithm (CPU custom-op path restated in oracle/) on the host cores: batch=1 per request, one
+    in-flight request per core (blaze-benchmark consumers).  This process loads oracle/ only -- the HNSW files it
+    searches are produced by the offline builder in a separate process when they are not cached yet."""
     if rank != 0:
         return None
-    import torch
     from oracle import oracle as orc
-    from nann_b200 import index as nix, scorer_weights as sw
-    dev = "cuda" if torch.cuda.is_available() else "cpu"
-    sh = get_shard(args.n_items, 1, 0, dev)
+    sw = _by_path("scorer_weights")
+    key_done = os.path.join(shard_dir(args.n_items, 1, 0), "done")
+    if args.n_items > 200_000 and not os.path.exists(key_done):
+        # index construction is offline tooling, not the timed path: run it out of process
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--build-index-only", "--n-items", str(args.n_items)],
+                           stdout=subprocess.DEVNULL, stderr=sys.stderr)
+        if r.returncode != 0:
+            log("[bench] out-of-process index build failed; building on the CPU")
+    sh = get_shard(args.n_items, 1, 0, "cpu")
     cores = os.cpu_count() or 1
     oix = orc.Index(sh["emb"], sh["item_ids"], sh["ep"].astype(np.int32), [v.astype(np.int32) for v in sh["values"]], sh["row_splits"])
     om = orc.Mlp(*sw.mlp_weights(seed=3))
     sample_q = args.cpu_sample or int(min(args.batch, max(32, 4 * cores)))
-    queries = nix.synthetic_queries(sh["emb"], sample_q * (args.steps + args.warmup), seed=2)
+    queries = nix().synthetic_queries(sh["emb"], sample_q * (args.steps + args.warmup), seed=2)
     for w in range(args.warmup):
         oix.search_batch_mlp(om, queries[w * sample_q:(w + 1) * sample_q], T, nthreads=cores)
     secs, rows = 0.0, 0
@@ -204,97 +294,182 @@ def run_reference(args, T, rank, world):
             "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 
 
-def workload_config(args, T, world):
-    which = {(1_000_000, 256, 200): "BASELINE configs[1]", (10_000_000, 1024, 400): "BASELINE configs[2]"}.get(
-        (args.n_items, args.batch, args.ef), "BASELINE configs[4] sweep point" if args.n_items == 1_000_000 else "custom")
-    if world > 1:
-        return {"workload": f"{world} x {args.n_items} items d=128 f32 (one {args.n_items}-row shard + its own HNSW per GPU), global batch="
-                            f"{args.batch * world} queries, scoring MLP 2x512, ef_search={args.ef} split over the shards, HNSW M=32 "
-                            f"(BASELINE configs[3] shape at {args.n_items} rows per GPU)",
-                "level_topn": list(T), "parallelism": f"corpus row-sharded x{world}: every query visits every shard, one NCCL allgather of "
-                                                      f"per-shard top-k + merge kernel; weak scaling (rows and queries per step grow with N)",
-                "l2": "inputs larger than L2: 512 MB embedding table + 260 MB graph per 1M rows, fresh queries every step"}
-    return {"workload": f"{args.n_items} items d=128 f32, batch={args.batch} queries, scoring MLP 2x512, "
-                        f"ef_search={args.ef}, HNSW M=32 ({which})",
-            "level_topn": list(T), "parallelism": "1 GPU",
-            "l2": "inputs larger than L2: 512 MB embedding table + 260 MB graph per 1M rows, fresh queries every step"}
+# ------------------------------------------------------------------------------------------------
+class Truth:
+    """brute-force top-k under the same scorer over the WHOLE corpus for the evaluation queries: every rank scores
+    its own rows with the product's scorer (nann_blaze_xla_run, device in/out), the per-shard top-k are gathered with
+    torch.distributed and merged on every rank (evaluation plumbing, outside the timed region)."""
+
+    def __init__(self, nb, sc, emb_dev, item_ids_dev, queries, k, world, dev):
+        import torch
+        import torch.distributed as dist
+        n = emb_dev.shape[0]
+        out = torch.empty(n, dtype=torch.float32, device=dev)
+        kk = min(k, n)
+        loc_s = torch.empty((len(queries), kk), dtype=torch.float32, device=dev)
+        loc_i = torch.empty((len(queries), kk), dtype=torch.int64, device=dev)
+        for q in range(len(queries)):
+            nb.blaze_xla_op(sc, queries[q], emb_dev, out=out)
+            s, i = torch.topk(out, kk)
+            loc_s[q], loc_i[q] = s, item_ids_dev[i]
+        if world > 1:
+            gs = [torch.empty_like(loc_s) for _ in range(world)]
+            gi = [torch.empty_like(loc_i) for _ in range(world)]
+            dist.all_gather(gs, loc_s); dist.all_gather(gi, loc_i)
+            cs, ci = torch.cat(gs, 1), torch.cat(gi, 1)
+            s, o = torch.topk(cs, k, dim=1)
+            loc_i = torch.gather(ci, 1, o)
+        self.ids = loc_i.cpu().numpy()
+        self.k = k
+
+    def recall(self, got_ids):
+        n = min(len(got_ids), len(self.ids))
+        hits = sum(len(set(self.ids[q].tolist()) & set(np.asarray(got_ids[q]).tolist())) for q in range(n))
+        return hits / (n * self.k)
 
 
 def run_b200(args, T, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     import nann_b200 as nb
-    from nann_b200 import index as nix, scorer_weights as sw
+    from nann_b200 import scorer_weights as sw
+    from nann_b200.distributed import ShardGroup
     torch.cuda.set_device(local_rank)
     dev = f"cuda:{local_rank}"
+    k = T[5]
     sh = get_shard(args.n_items, world, rank, dev)
-    Ts = shard_topn(T, world)
     ix = nb.Index.from_arrays(sh["emb"], sh["item_ids"], sh["ep"], sh["values"], sh["row_splits"], device=local_rank)
     sc = nb.Scorer.mlp(*sw.mlp_weights(seed=3), device=local_rank)
     if args.precision == "tensor":
         sc.set_precision(nb.SCORER_TENSOR)
     B = args.batch * world          # N > 1: the global batch grows with N and every shard sees all of it
-    se = nb.Searcher(ix, sc, B, Ts)
-    k_s, k = Ts[5], T[5]
     n_steps = args.warmup + args.steps
-    # every rank draws the same queries (from block 0 of the sharded corpus)
-    full = sh["emb"] if (world == 1 or rank == 0) else corpus_block(args.n_items, 0)[0]
-    queries = nix.synthetic_queries(full, B * n_steps, seed=2)
-    del full
-    q_dev = torch.from_numpy(queries).to(dev)
-    q_pin = torch.from_numpy(queries).pin_memory()
-    ids_d = torch.empty((B, k_s), dtype=torch.int64, device=dev)
-    sc_d = torch.empty((B, k_s), dtype=torch.float32, device=dev)
-    if world > 1:
-        g_ids = torch.empty((world * B, k_s), dtype=torch.int64, device=dev)
-        g_sc = torch.empty((world * B, k_s), dtype=torch.float32, device=dev)
-        m_ids = torch.empty((B, k), dtype=torch.int64, device=dev)
-        m_sc = torch.empty((B, k), dtype=torch.float32, device=dev)
-    stream = torch.cuda.current_stream()
-
-    dbg = {"search_ms": 0.0, "exchange_ms": 0.0, "merge_ms": 0.0} if os.environ.get("NANN_BENCH_DEBUG") else None
-
-    def step_device(i):
-        if dbg is not None and world > 1:      # per-phase wall clock with synchronisation (debug only: serialises the step)
-            t0 = time.perf_counter()
-            se.search_device(q_dev[i * B:(i + 1) * B], Ts, ids_d, sc_d, stream=stream); torch.cuda.synchronize()
-            t1 = time.perf_counter()
-            dist.all_gather_into_tensor(g_sc, sc_d); dist.all_gather_into_tensor(g_ids, ids_d); torch.cuda.synchronize()
-            t2 = time.perf_counter()
-            r = nb.merge_topk(g_sc.view(world, B, k_s), g_ids.view(world, B, k_s), k)
-            t3 = time.perf_counter()
-            dbg["search_ms"] += 1e3 * (t1 - t0); dbg["exchange_ms"] += 1e3 * (t2 - t1); dbg["merge_ms"] += 1e3 * (t3 - t2)
-            return r
-        status, _ = se.search_device(q_dev[i * B:(i + 1) * B], Ts, ids_d, sc_d, stream=stream)
-        if world > 1:     # inputs and the merged result stay in HBM
-            dist.all_gather_into_tensor(g_sc, sc_d)
-            dist.all_gather_into_tensor(g_ids, ids_d)
-            return nb.merge_topk(g_sc.view(world, B, k_s), g_ids.view(world, B, k_s), k, out_scores=m_sc, out_ids=m_ids)
-        return status
-
-    q_step = torch.empty((B, 128), dtype=torch.float32, device=dev)
-
-    def step_e2e(i):
-        # host buffers in, host results out: H2D of the queries and D2H of ids+scores inside the timed region
-        if world == 1:
-            return se.search(q_pin[i * B:(i + 1) * B].numpy(), Ts)
-        # sharded: pinned queries -> device, shard search, NCCL allgather, merge kernel, merged top-k -> host
-        q_step.copy_(q_pin[i * B:(i + 1) * B], non_blocking=True)
-        se.search_device(q_step, Ts, ids_d, sc_d, stream=stream)
-        dist.all_gather_into_tensor(g_sc, sc_d)
-        dist.all_gather_into_tensor(g_ids, ids_d)
-        return nb.merge_topk(g_sc.view(world, B, k_s), g_ids.view(world, B, k_s), k)   # host arrays (D2H inside)
+    pool = query_pool(args.n_items)                     # every rank draws the same queries
+    queries = nix().synthetic_queries(pool, B * n_steps, seed=2)
+    n_eval = max(0, args.eval_queries)
+    eval_q = nix().synthetic_queries(pool, max(n_eval, 1), seed=5)
+    del pool
+    stream = torch.cuda.Stream(device=dev)              # a non-blocking stream (the legacy default stream serialises with every other stream)
+    extra = {}
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- recall bookkeeping (outside the timed region): brute-force truth, the one-GPU operating point, calibration
+    truth = None
+    if n_eval > 0:
+        t0 = time.time()
+        emb_dev = torch.from_numpy(sh["emb"]).to(dev)           # evaluation copy (the index owns its own)
+        truth = Truth(nb, sc, emb_dev, torch.from_numpy(sh["item_ids"]).to(dev), eval_q, k, world, dev)
+        del emb_dev
+        torch.cuda.empty_cache()
+        log(f"[bench] rank {rank}: brute-force truth for {n_eval} queries in {time.time() - t0:.1f}s")
+
+    grp, exchange = None, "none (1 GPU)"
+    Ts, scale = list(T), 1.0
+    if world > 1:
+        k_s_max = min(k, 4096 // world * 2)
+        grp = ShardGroup(rank, world, max(B, n_eval), k_s_max, device=local_rank)
+        try:
+            grp.connect_torch()
+            exchange = "in-library: final top-k kernel stores (score,id) records into every rank's window over NVLink (CUDA IPC peer mappings), merge kernel on the group's stream"
+        except Exception as e:                                   # no peer mappings in this container: NCCL transport
+            log(f"[bench] rank {rank}: peer windows unavailable ({e!r}); falling back to torch.distributed all_gather")
+            grp = None
+            exchange = f"torch.distributed all_gather + nann_merge_topk (peer windows unavailable: {str(e)[:120]})"
+        ok = torch.tensor([1.0 if grp is not None else 0.0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() == 0.0 and grp is not None:                # all ranks must use the same transport
+            grp = None
+            exchange = "torch.distributed all_gather + nann_merge_topk (a peer could not map the windows)"
+
+    def sharded_host(se, users_np, Ts_):
+        """host queries in, merged host ids out, every rank the same result"""
+        if grp is not None:
+            sc_, ids_, st_ = grp.search(se, users_np, Ts_, k)
+            return ids_, sc_, st_
+        from nann_b200 import distributed as nd
+        u = torch.from_numpy(users_np).to(dev)
+        o_i = torch.empty((len(users_np), Ts_[5]), dtype=torch.int64, device=dev)
+        o_s = torch.empty((len(users_np), Ts_[5]), dtype=torch.float32, device=dev)
+        m_sc, m_id, st_, _ = nd.sharded_search(se, u, Ts_, k, o_i, o_s, nb.merge_topk)
+        return m_id, m_sc, st_
+
+    recall_target = None
+    if world > 1 and truth is not None and args.shard_scale <= 0:
+        # the one-GPU operating point: rank 0 searches the UNSHARDED index with the full beams
+        if args.n_items <= BIG:
+            rt = torch.zeros(1, dtype=torch.float64, device=dev)
+            if rank == 0:
+                t0 = time.time()
+                sh1 = get_shard(args.n_items, 1, 0, dev)
+                ix1 = nb.Index.from_arrays(sh1["emb"], sh1["item_ids"], sh1["ep"], sh1["values"], sh1["row_splits"], device=local_rank)
+                se1 = nb.Searcher(ix1, sc, n_eval, T)
+                rt[0] = truth.recall(se1.search(eval_q[:n_eval], T)["ids"])
+                del se1, ix1, sh1
+                log(f"[bench] one-GPU operating point: recall@{k} = {rt.item():.4f} ({time.time() - t0:.1f}s)")
+            dist.broadcast(rt, 0)
+            recall_target = rt.item()
+        # smallest per-shard beam scale that holds it
+        trials = []
+        for s_ in SCALES:
+            Ts_ = shard_topn(T, world, s_)
+            se_ = nb.Searcher(ix, sc, n_eval, Ts_)
+            rec = truth.recall(sharded_host(se_, eval_q[:n_eval], Ts_)[0])
+            del se_
+            trials.append({"scale": s_, "shard_level_topn": Ts_, "recall": rec})
+            Ts, scale = Ts_, s_
+            if recall_target is None or rec >= recall_target - RECALL_TOL:
+                break
+        extra["calibration"] = trials
+    elif world > 1:
+        scale = args.shard_scale if args.shard_scale > 0 else 1.0
+        Ts = shard_topn(T, world, scale)
+
+    se = nb.Searcher(ix, sc, B, Ts)
+    k_s = Ts[5]
+    q_dev = torch.from_numpy(queries).to(dev)
+    q_pin = torch.from_numpy(queries).pin_memory()
+    outs = [(torch.empty((B, k), dtype=torch.int64, device=dev), torch.empty((B, k), dtype=torch.float32, device=dev),
+             torch.empty((B,), dtype=torch.int32, device=dev)) for _ in range(2)]
+    if world > 1 and grp is None:
+        from nann_b200 import distributed as nd
+        ids_d = torch.empty((B, k_s), dtype=torch.int64, device=dev)
+        sc_d = torch.empty((B, k_s), dtype=torch.float32, device=dev)
+
+    def step_device(i):
+        """inputs resident in HBM, results left in HBM, nothing synchronises the host"""
+        u = q_dev[i * B:(i + 1) * B]
+        if world == 1:
+            se.search_async(u, Ts, *outs[i & 1], stream=stream)
+        elif grp is not None:
+            grp.search(se, u, Ts, k, *outs[i & 1], stream=stream)
+        else:
+            nd.sharded_search(se, u, Ts, k, ids_d, sc_d, nb.merge_topk, stream=stream)
+
+    p_ids = torch.empty((B, k_s), dtype=torch.int64, device=dev)
+    p_sc = torch.empty((B, k_s), dtype=torch.float32, device=dev)
+
+    def step_profile(i):
+        """the same step (this rank's shard search) through the call that returns the per-stage CUDA-event clocks;
+        it synchronises every step, which is why it is not the pass `value` is taken from"""
+        se.search_device(q_dev[i * B:(i + 1) * B], Ts, p_ids, p_sc, stream=stream)
+
+    def step_e2e(i):
+        # host buffers in, host results out: H2D of the queries and D2H of ids+scores inside the timed region
+        if world == 1:
+            return se.search(q_pin[i * B:(i + 1) * B].numpy(), Ts)
+        return sharded_host(se, q_pin[i * B:(i + 1) * B].numpy(), Ts)
+
     step_wall = []
 
-    def timed(fn, profile):
+    def timed(fn, profile, drain=False):
         for w in range(args.warmup):
             fn(w)
+        if drain and grp is not None:
+            grp.wait()
         barrier()
         se.set_profile(profile)
         l0 = nb.launch_count()
@@ -307,6 +482,8 @@ def run_b200(args, T, rank, world, local_rank):
             ts = time.perf_counter()
             fn(args.warmup + s)
             step_wall.append(time.perf_counter() - ts)
+        if drain and grp is not None:
+            grp.wait(stream=stream, host_block=False)      # the timed region ends when the last merge has run
         e1.record(stream)
         barrier()
         wall = time.perf_counter() - t0
@@ -319,51 +496,68 @@ def run_b200(args, T, rank, world, local_rank):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t[0].item(), t[1].item(), nb.launch_count() - l0, prof
 
+    nvl0 = nvlink_tx_rx_kib(local_rank) if (world > 1 and rank == 0) else None
     with ClockSampler(local_rank) as clk:
-        dev_ms, _, launches, prof = timed(step_device, True)
+        dev_ms, _, launches, _ = timed(step_device, False, drain=True)
         clk.window(*timed.window)
+    nvl1 = nvlink_tx_rx_kib(local_rank) if (world > 1 and rank == 0) else None
+    # stage clocks (scorer launches for the roofline): the same steps with CUDA events around every stage
+    prof_ms, _, _, prof = timed(step_profile, True)
     e2e_dev_ms, e2e_wall_ms, _, _ = timed(step_e2e, False)
     # the public call is synchronous (host results are returned), so a step's wall time is the batch latency
     lat = sorted(step_wall)
     latency_ms = {"p50": 1000.0 * lat[len(lat) // 2], "max": 1000.0 * lat[-1], "batch": B,
                   "what": "wall time of one public API call (host queries in, host ids+scores out)"}
 
-    # ---- outside the timed region: recall@200 vs brute force under the same scorer; parity vs the CPU port
-    extra = {}
+    # ---- recall@k of the measured configuration (outside the timed region)
     try:
-        n_eval = min(args.eval_queries, B)
-        if n_eval <= 0:
+        if truth is None:
             raise RuntimeError("recall evaluation disabled (--eval-queries 0)")
+        se_e = nb.Searcher(ix, sc, n_eval, Ts) if n_eval > B else se
+        got = se_e.search(eval_q[:n_eval], Ts)["ids"] if world == 1 else sharded_host(se_e, eval_q[:n_eval], Ts)[0]
+        extra["recall_at_k_vs_bruteforce"] = truth.recall(got)
+        extra["recall_queries"] = n_eval
         if world > 1:
-            n_eval = min(n_eval, 4)
-        res = step_e2e(0)                                # all ranks take part (collective inside)
-        got_ids = (res[1] if world > 1 else res["ids"])[:n_eval]
-        if rank == 0:
-            best_s = [np.empty(0, np.float32) for _ in range(n_eval)]
-            best_i = [np.empty(0, np.int64) for _ in range(n_eval)]
-            for b in range(world):                       # brute force over the WHOLE corpus, one block at a time
-                emb_b, ids_b = (sh["emb"], sh["item_ids"]) if b == rank else corpus_block(args.n_items, b)
-                emb_t = torch.from_numpy(emb_b).to(dev)
-                for q in range(n_eval):
-                    s_all = nb.blaze_xla_op(sc, queries[q], emb_t)
-                    top = np.argpartition(-s_all, k)[:k]
-                    cs, ci = np.concatenate([best_s[q], s_all[top]]), np.concatenate([best_i[q], ids_b[top]])
-                    keep = np.argsort(-cs, kind="stable")[:k]
-                    best_s[q], best_i[q] = cs[keep], ci[keep]
-                del emb_t
-            hits = sum(len(set(best_i[q].tolist()) & set(got_ids[q].tolist())) for q in range(n_eval))
-            extra["recall_at_k_vs_bruteforce"] = hits / (n_eval * k)
-            extra["recall_queries"] = n_eval
+            extra["recall_target"] = recall_target
+            extra["recall_target_source"] = ("the unsharded index searched with the full beams on rank 0, same queries, this run"
+                                             if recall_target is not None else "none (corpus too large for one unsharded index build here)")
+            extra["recall_held"] = bool(recall_target is not None and extra["recall_at_k_vs_bruteforce"] >= recall_target - RECALL_TOL)
+            extra["shard_beam_scale"] = scale
     except Exception as e:  # never lose the bench line over the side measurements
         extra["recall_error"] = repr(e)[:200]
+
+    # ---- replica mode (SURVEY 8e alternative; what the reference's session pool does): the WHOLE index on every GPU,
+    # --batch queries per GPU, no exchange
+    if world > 1 and args.n_items <= BIG and not args.no_replica:
+        try:
+            if rank == 0:
+                get_shard(args.n_items, 1, 0, dev)               # cached by the recall-target pass; builds otherwise
+            barrier()
+            sh1 = get_shard(args.n_items, 1, 0, dev)
+            ix1 = nb.Index.from_arrays(sh1["emb"], sh1["item_ids"], sh1["ep"], sh1["values"], sh1["row_splits"], device=local_rank)
+            se1 = nb.Searcher(ix1, sc, args.batch, T)
+            o1 = [(torch.empty((args.batch, k), dtype=torch.int64, device=dev), torch.empty((args.batch, k), dtype=torch.float32, device=dev))
+                  for _ in range(2)]
+            b1 = args.batch
+
+            def step_replica(i):       # rank r serves its own slice of the global batch
+                u = q_dev[i * B + rank * b1:i * B + (rank + 1) * b1]
+                se1.search_async(u, T, *o1[i & 1], stream=stream)
+
+            r_ms, _, _, _ = timed(step_replica, False)
+            extra["replica_mode"] = {"value": B * args.steps / (r_ms / 1000.0), "unit": "queries/s", "ms_per_step": r_ms / args.steps,
+                                     "what": f"whole {args.n_items}-row index on every GPU, {b1} queries per GPU and step, no exchange "
+                                             f"(the reference's replica model, blaze-benchmark/benchmark/core/model.cc:192-234); recall = the one-GPU operating point"}
+            del se1, ix1, sh1
+        except Exception as e:
+            extra["replica_mode"] = {"error": repr(e)[:200]}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:   # cpu_baseline: rank 0 at N=1 only
         try:
             from oracle import oracle as orc
             cores = os.cpu_count() or 1
-            sh1 = sh
-            oix = orc.Index(sh1["emb"], sh1["item_ids"], sh1["ep"].astype(np.int32), [v.astype(np.int32) for v in sh1["values"]], sh1["row_splits"])
+            oix = orc.Index(sh["emb"], sh["item_ids"], sh["ep"].astype(np.int32), [v.astype(np.int32) for v in sh["values"]], sh["row_splits"])
             om = orc.Mlp(*sw.mlp_weights(seed=3))
             n_warm = int(min(len(queries), max(32, 2 * cores)))
             rw = oix.search_batch_mlp(om, queries[:n_warm], T, nthreads=cores)   # warm + rate estimate
@@ -373,28 +567,29 @@ def run_b200(args, T, rank, world, local_rank):
             cpu = {"value": sample_q / r["seconds"], "unit": "queries/s", "cores": cores, "kind": "port",
                    "sample": f"first {sample_q} queries of the run, one request per core (batch=1 each), {r['seconds']:.1f}s",
                    "rows_scored_per_query": r["n_scored"] / sample_q}
-            if world == 1:
-                n_cmp = min(sample_q, B)                 # the searcher was created for batches of B
-                mine = se.search(queries[:n_cmp], T)
-                r = {k2: (v2[:n_cmp] if isinstance(v2, np.ndarray) else v2) for k2, v2 in r.items()}
-                cpu["compared_queries"] = n_cmp
-                cpu["ids_equal_to_gpu"] = bool(np.array_equal(mine["ids"], r["ids"]))
-                cpu["topk_overlap_with_gpu"] = float(np.mean([len(set(a.tolist()) & set(b.tolist())) / max(k, 1)
-                                                              for a, b in zip(mine["ids"], r["ids"])]))
-                both = [(a, b) for a, b in zip(mine["ids"], r["ids"])]
-                diffs = []
-                for qi, (a, b) in enumerate(both):        # scores of items both paths returned
-                    pa = {int(i): float(s_) for i, s_ in zip(a, mine["scores"][qi])}
-                    diffs += [abs(pa[int(i)] - float(s_)) for i, s_ in zip(b, r["scores"][qi]) if int(i) in pa]
-                cpu["max_abs_score_diff_common_items"] = float(max(diffs)) if diffs else None
-                if args.precision == "tensor":            # the bit-exact path, for the record
-                    sc.set_precision(nb.SCORER_EXACT)
-                    ex = se.search(queries[:n_cmp], T)
-                    sc.set_precision(nb.SCORER_TENSOR)
-                    cpu["exact_path_ids_equal_to_cpu"] = bool(np.array_equal(ex["ids"], r["ids"]))
-                    cpu["exact_path_scores_bit_equal"] = bool(np.array_equal(ex["scores"].view(np.uint32), r["scores"].view(np.uint32)))
+            n_cmp = min(sample_q, B)                 # the searcher was created for batches of B
+            mine = se.search(queries[:n_cmp], T)
+            r = {k2: (v2[:n_cmp] if isinstance(v2, np.ndarray) else v2) for k2, v2 in r.items()}
+            cpu["compared_queries"] = n_cmp
+            cpu["ids_equal_to_gpu"] = bool(np.array_equal(mine["ids"], r["ids"]))
+            cpu["topk_overlap_with_gpu"] = float(np.mean([len(set(a.tolist()) & set(b.tolist())) / max(k, 1)
+                                                          for a, b in zip(mine["ids"], r["ids"])]))
+            diffs = []
+            for qi, (a, b) in enumerate(zip(mine["ids"], r["ids"])):        # scores of items both paths returned
+                pa = {int(i): float(s_) for i, s_ in zip(a, mine["scores"][qi])}
+                diffs += [abs(pa[int(i)] - float(s_)) for i, s_ in zip(b, r["scores"][qi]) if int(i) in pa]
+            cpu["max_abs_score_diff_common_items"] = float(max(diffs)) if diffs else None
+            if args.precision == "tensor":            # the bit-exact path, for the record
+                sc.set_precision(nb.SCORER_EXACT)
+                ex = se.search(queries[:n_cmp], T)
+                sc.set_precision(nb.SCORER_TENSOR)
+                cpu["exact_path_ids_equal_to_cpu"] = bool(np.array_equal(ex["ids"], r["ids"]))
+                cpu["exact_path_scores_bit_equal"] = bool(np.array_equal(ex["scores"].view(np.uint32), r["scores"].view(np.uint32)))
         except Exception as e:
             cpu = {"error": repr(e)[:200]}
+    if grp is not None:
+        barrier()
+        grp.close()
     if rank != 0:
         return None
 
@@ -405,14 +600,17 @@ def run_b200(args, T, rank, world, local_rank):
     n_score = max(prof["launches"]["score"], 1)
     ach_tf = rows * 2.0 * MAC_PER_ROW / (score_ms / 1000.0) / 1e12 if score_ms > 0 else 0.0
     stage_tot = sum(prof["ms"].values())
+    held = extra.get("recall_held", True) if world > 1 else True
     out = {
-        "metric": "queries/sec at fixed recall@200", "value": qps, "unit": "queries/s", "n_gpus": world,
+        "metric": "queries/sec at fixed recall@200" if held else "queries/sec (recall NOT held at the one-GPU operating point, see recall_*)",
+        "value": qps, "unit": "queries/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": dict(workload_config(args, T, world), shard_level_topn=Ts, scorer_precision=args.precision),
+        "exchange": exchange,
         "e2e": {"value": B * args.steps / (e2e_wall_ms / 1000.0), "unit": "queries/s",
                 "h2d_bytes_per_step": B * 128 * 4,
-                "d2h_bytes_per_step": (B * k_s * 12 + B * 4 + 10 * B * 4) if world == 1 else B * k * 12,
+                "d2h_bytes_per_step": (B * k * 12 + B * 4 + 10 * B * 4) if world == 1 else B * k * 12 + B * 4,
                 "timing": "wall clock around the public API call with pinned host inputs and host outputs",
                 "device_ms_per_step": e2e_dev_ms / args.steps},
         "latency_ms": latency_ms,
@@ -428,24 +626,39 @@ def run_b200(args, T, rank, world, local_rank):
             "issued_mma_tflops": (3.0 * ach_tf * (2 * (128 * 512 + 512 * 512)) / (2.0 * MAC_PER_ROW)) if args.precision == "tensor" else None,
             "note": "tensor precision issues 3 fp16 MMAs per fp32 product (hi/lo split, |dscore| <= 1e-5); the layer-1 user half is hoisted per query",
             "avg_launch_ms": score_ms / n_score,
+            "timed_with": "CUDA events around every scorer launch, in a second pass over the same steps (the value pass runs without events or host syncs)",
             "gather_GBps_inside_kernel": rows * ROW_BYTES / (score_ms / 1000.0) / 1e9 if score_ms > 0 else 0.0,
             "hbm_peak_GBps": pk["hbm_gbs"]},
+        "roofline_gather": _gather_roofline(),
         "stages_ms_per_step": {k2: v / args.steps for k2, v in prof["ms"].items()},
         "stage_share": {k2: (v / stage_tot if stage_tot else 0) for k2, v in prof["ms"].items()},
-        "rows_scored_per_query": rows / (B * args.steps),
+        "profile_pass_ms_per_step": prof_ms / args.steps,
+        "rows_scored_per_query": rows / (B * args.steps) * world,
+        "rows_scored_per_query_per_shard": rows / (B * args.steps),
         "cpu_baseline": cpu,
     }
+    if nvl0 and nvl1:
+        out["nvlink"] = {"tx_kib_rank0": nvl1[0] - nvl0[0], "rx_kib_rank0": nvl1[1] - nvl0[1],
+                         "what": "nvidia-smi nvlink -gt d on GPU 0, delta over warm-up + timed steps of the device-resident pass",
+                         "expected_tx_kib_per_step": B * k_s * 12 * (world - 1) / 1024.0, "steps_counted": n_steps}
     out.update(extra)
-    if dbg is not None:
-        out["debug"] = {k2: v / (args.steps + args.warmup) for k2, v in dbg.items()}
     return out
 
 
 def _ncu_traffic(precision):
     """DRAM bytes of one launch of the dominant kernel, from the committed `ncu --set full` capture (profiles/)."""
     try:
-        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             return json.load(f)[precision]["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
+def _gather_roofline():
+    """the standalone embedding-row gather (GatherV2) against the HBM roofline, from the committed ncu capture"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "gather_roofline.json")) as f:
+            return json.load(f)
     except Exception:
         return None
 
@@ -457,12 +670,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n-items", type=int, default=1_000_000)
-    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--batch", type=int, default=256, help="queries per GPU and step")
     ap.add_argument("--ef", type=int, default=200, choices=[200, 400])
     ap.add_argument("--precision", default=os.environ.get("NANN_BENCH_PRECISION", "tensor"), choices=["exact", "tensor"])
-    ap.add_argument("--eval-queries", type=int, default=16)
+    ap.add_argument("--eval-queries", type=int, default=128, help="queries of the recall@k measurement / calibration")
+    ap.add_argument("--shard-scale", type=float, default=0.0, help="N>1: fix the per-shard beam scale instead of calibrating it")
+    ap.add_argument("--no-replica", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--build-index-only", action="store_true", help="build + cache the unsharded index files and exit (offline tooling)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     T = EF_TOPN[args.ef]
@@ -480,6 +696,10 @@ def main():
         sys.stdout.flush()
         os.write(real_stdout, (json.dumps(obj) + "\n").encode())
 
+    if args.build_index_only:
+        import torch
+        get_shard(args.n_items, 1, 0, "cuda:0" if torch.cuda.is_available() else "cpu")
+        return
     if args.impl == "reference":
         out = run_reference(args, T, rank, world)
         if out is not None:

@@ -522,16 +522,19 @@ static nann_status search_enqueue(nann_searcher* s, const float* users, int B, c
   const int64_t mb = s->max_batch;
   const int k = T[5];
 
-  // users -> device workspace (H2D when the caller passed host memory)
-  NANN_CUDA(cudaMemcpyAsync(s->users, users, (size_t)B * uf * 4,
-                            is_device_ptr(users) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
-  NANN_CUDA(cudaMemsetAsync(s->status, 0, (size_t)B * 4, st));
-  NANN_CUDA(cudaMemsetAsync(s->round_n, 0, (size_t)5 * mb * 4, st));
-  NANN_CUDA(cudaMemsetAsync(s->round_exp, 0, (size_t)5 * mb * 4, st));
-  if (k > 0) {
-    NANN_CUDA(cudaMemsetAsync(s->out_item, 0xFF, (size_t)B * k * 8, st));
-    NANN_CUDA(cudaMemsetAsync(s->out_sc, 0xFF, (size_t)B * k * 4, st));
-    NANN_CUDA(cudaMemsetAsync(s->out_nodes, 0xFF, (size_t)B * k * 4, st));
+  // users -> device workspace (H2D when the caller passed host memory; inside the init kernel otherwise) and the
+  // per-call state, in ONE kernel (no memset nodes: see fill_words_kernel)
+  const bool users_dev = is_device_ptr(users);
+  if (!users_dev) NANN_CUDA(cudaMemcpyAsync(s->users, users, (size_t)B * uf * 4, cudaMemcpyHostToDevice, st));
+  {
+    SearchInitArgs ia{};
+    ia.status = s->status; ia.B = B;
+    ia.round_n = s->round_n; ia.round_exp = s->round_exp; ia.n_round = 5 * mb;
+    ia.out_item_w = (uint32_t*)s->out_item; ia.out_sc_w = (uint32_t*)s->out_sc; ia.out_nodes_w = (uint32_t*)s->out_nodes;
+    ia.n_out = (int64_t)B * k;
+    ia.users_src = users_dev ? users : nullptr; ia.users_dst = s->users; ia.n_users = (int64_t)B * uf;
+    const int64_t work = std::max<int64_t>(std::max<int64_t>(ia.n_round, ia.n_out), ia.n_users);
+    NANN_LAUNCH(search_init_kernel, (unsigned)std::min<int64_t>(ceil_div(work, 256), 148 * 4), 256, 0, st, ia);
   }
   NANN_TRY(scorer_prepare_users(s->sc, s->users, B, s->ustate, st));
 
@@ -597,7 +600,7 @@ static nann_status search_enqueue(nann_searcher* s, const float* users, int B, c
   };
   auto mark = [&](const int32_t* list, int64_t stride, int n) -> nann_status {
     t_begin(3);
-    NANN_CUDA(cudaMemsetAsync(s->bitmap, 0, (size_t)B * s->n_words * 4, st));  // Assign zeros :118,:131
+    NANN_LAUNCH(fill_words_kernel, 148 * 8, 256, 0, st, s->bitmap, (int64_t)B * s->n_words, 0u);  // Assign zeros :118,:131
     if (n > 0)
       NANN_LAUNCH(mark_kernel, (unsigned)ceil_div((int64_t)B * n, 256), 256, 0, st, list, stride, n, s->bitmap,
                   s->n_words, s->status, B);

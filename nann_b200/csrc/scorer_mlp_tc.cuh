@@ -97,9 +97,8 @@ static nann_status mlp_tc_score(nann_scorer* s, const ScoreCall& c, cudaStream_t
   static const int cta_cap = [] { const char* e = std::getenv("NANN_TC_CTAS"); return e ? atoi(e) : 1 << 30; }();   // debug
   // a dense tile list gives every cluster the same number of tiles however ragged the per-query counts are
   NANN_LAUNCH(tile_scan_kernel, 1, 1024, 0, stm, c.n_ptr, c.n_fixed, c.status, c.B, c.ws->tile_start);
-  NANN_LAUNCH(tile_fill_kernel, c.B, 128, 0, stm, c.ws->tile_start, c.B, c.ws->tiles);
-  // cluster pairs, both CTAs on the same tile; the two CTAs red.add their partial scores into out
-  NANN_CUDA(cudaMemset2DAsync(c.out, (size_t)c.out_stride * sizeof(float), 0, (size_t)c.max_n * sizeof(float), (size_t)c.B, stm));
+  // cluster pairs, both CTAs on the same tile; the two CTAs red.add their partial scores into out (zeroed here)
+  NANN_LAUNCH(tile_fill_kernel, c.B, 256, 0, stm, c.ws->tile_start, c.B, c.ws->tiles, c.n_ptr, c.n_fixed, c.out, c.out_stride);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(std::min(st->n_ctas, cta_cap) / 2 * 2));
   cfg.blockDim = dim3(T8_THREADS);

@@ -290,10 +290,16 @@ tile_scan_kernel(const int32_t* __restrict__ n_ptr, int n_fixed, const int32_t* 
   }
   if (tid == 0) tile_start[B] = carry;
 }
-__global__ void tile_fill_kernel(const int32_t* __restrict__ tile_start, int B, int2* __restrict__ tiles) {
+// also zeroes the query's score row: the two CTAs of a cluster red.add their partial scores into it
+__global__ void tile_fill_kernel(const int32_t* __restrict__ tile_start, int B, int2* __restrict__ tiles,
+                                 const int32_t* __restrict__ n_ptr, int n_fixed, float* __restrict__ out, int64_t out_stride) {
   const int q = blockIdx.x;
   const int s = tile_start[q], e = tile_start[q + 1];
   for (int t = threadIdx.x; t < e - s; t += blockDim.x) tiles[s + t] = make_int2(q, t);
+  if (e == s) return;                              // failed or empty query: no tile, nothing is added
+  const int n = n_ptr ? n_ptr[q] : n_fixed;
+  float* row = out + (int64_t)q * out_stride;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) row[i] = 0.f;
 }
 
 

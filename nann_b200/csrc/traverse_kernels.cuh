@@ -268,6 +268,36 @@ expand_filter_cta_kernel(const int32_t* __restrict__ nbr_vals, const int64_t* __
   if (tid == 0) { out_n[q] = o; out_exp[q] = total; }
 }
 
+// ---- fills as kernels.  cudaMemsetAsync / device-to-device cudaMemcpyAsync are "implicit synchronisation" points
+// between streams on some driver paths (CUDA programming guide, "Implicit Synchronization"): a memset of one
+// searcher could not start while another stream's kernel -- e.g. the shard group's flag-wait kernel -- was still
+// running.  Kernels have no such coupling, and they fold into a CUDA graph as ordinary nodes.
+__global__ void fill_words_kernel(uint32_t* __restrict__ p, int64_t n_words, uint32_t v) {
+  const int64_t n4 = n_words >> 2;            // p is 16-byte aligned (cudaMalloc + row sizes in words: callers check)
+  uint4* p4 = reinterpret_cast<uint4*>(p);
+  const uint4 v4 = make_uint4(v, v, v, v);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) p4[i] = v4;
+  for (int64_t i = (n4 << 2) + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_words; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+// start of a search call: status/round counters = 0, result slabs = 0xFF (ids -1, scores NaN pattern), and the
+// users copy when the caller's batch already lives in device memory
+struct SearchInitArgs {
+  int32_t* status; int B;
+  int32_t* round_n; int32_t* round_exp; int64_t n_round;     // 5 * max_batch
+  uint32_t* out_item_w; uint32_t* out_sc_w; uint32_t* out_nodes_w; int64_t n_out;   // B*k (out_item: 2 words each)
+  const float* users_src; float* users_dst; int64_t n_users; // nullptr src: copied by the host (H2D)
+};
+__global__ void search_init_kernel(SearchInitArgs a) {
+  const int64_t t0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, step = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = t0; i < a.B; i += step) a.status[i] = 0;
+  for (int64_t i = t0; i < a.n_round; i += step) { a.round_n[i] = 0; a.round_exp[i] = 0; }
+  for (int64_t i = t0; i < a.n_out; i += step) {
+    a.out_item_w[2 * i] = 0xFFFFFFFFu; a.out_item_w[2 * i + 1] = 0xFFFFFFFFu;
+    a.out_sc_w[i] = 0xFFFFFFFFu; a.out_nodes_w[i] = 0xFFFFFFFFu;
+  }
+  if (a.users_src) for (int64_t i = t0; i < a.n_users; i += step) a.users_dst[i] = a.users_src[i];
+}
+
 // ---- mark: set the bits of list[q][0..n) (set_difference on a list that is already unique:
 // build_opt_graph.py:119-120,132-133).  One thread per (q, i).
 __global__ void mark_kernel(const int32_t* __restrict__ list, int64_t stride, int n,

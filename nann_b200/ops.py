@@ -325,9 +325,10 @@ class Scorer:
             pass
 
 
-def blaze_xla_op(scorer, user, item_emb, stream=None):
+def blaze_xla_op(scorer, user, item_emb, stream=None, out=None):
     """tf.blaze_xla_op([user_seq_emb, item_emb], ...)[0] squeezed: logits f32[n]
-    (blaze_xla_kernel.cc:24-33; build_opt_graph.py:95-107)."""
+    (blaze_xla_kernel.cc:24-33; build_opt_graph.py:95-107).  `out`: optional f32 [n] CUDA tensor for the logits
+    (then nothing crosses PCIe and `out` is returned)."""
     u, _, k0 = _as(np.asarray(user, np.float32).reshape(-1) if not _is_torch(user) else user.float().reshape(-1), np.float32)
     if _is_torch(item_emb):
         x = item_emb.contiguous().float()
@@ -335,6 +336,11 @@ def blaze_xla_op(scorer, user, item_emb, stream=None):
     else:
         x = np.ascontiguousarray(item_emb, np.float32)
         n, ptr, k1 = x.shape[0], C.c_void_p(x.ctypes.data), x
+    if out is not None:
+        if not (_is_torch(out) and out.is_cuda and out.is_contiguous() and str(out.dtype).endswith("float32") and out.numel() == n):
+            raise TypeError(f"out must be a contiguous CUDA float32 tensor with {n} elements")
+        check(_lib.lib().nann_blaze_xla_run(scorer._h, u, ptr, n, C.c_void_p(out.data_ptr()), _stream_ptr(stream)))
+        return out
     out = np.empty(n, np.float32)
     check(_lib.lib().nann_blaze_xla_run(scorer._h, u, ptr, n, C.c_void_p(out.ctypes.data), _stream_ptr(stream)))
     return out

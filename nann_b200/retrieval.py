@@ -177,6 +177,28 @@ class Searcher:
         return status, dict(n_scored=np.array(st.n_scored[:], np.int64), n_expanded=np.array(st.n_expanded[:], np.int64),
                             n_failed=int(st.n_failed))
 
+    def search_async(self, users, level_topn, out_ids, out_scores, out_status=None, stream=None):
+        """Enqueue-only form: CUDA tensors in and out (out_status: optional i32 [B] CUDA tensor), no host
+        synchronisation and no counters; results are complete when work ordered after it on `stream` runs."""
+        uf = self.scorer.user_floats
+        if not (ops._is_torch(users) and users.is_cuda and users.dtype.is_floating_point):
+            raise TypeError("search_async: users must be a floating-point CUDA tensor")
+        u = users.contiguous().float().reshape(-1, uf)
+        B = u.shape[0]
+        k = max(int(level_topn[5]), 0)
+        for t, dt, shape, name in ((out_ids, "int64", (B, k), "out_ids"), (out_scores, "float32", (B, k), "out_scores"),
+                                   (out_status, "int32", (B,), "out_status")):
+            if t is None and name == "out_status":
+                continue
+            if not (ops._is_torch(t) and t.is_cuda and t.is_contiguous() and str(t.dtype).endswith(dt) and tuple(t.shape) == shape):
+                raise TypeError(f"search_async: {name} must be a contiguous CUDA {dt} tensor of shape {shape}")
+        T = (C.c_int32 * 6)(*[int(t) for t in level_topn])
+        check(_lib.lib().nann_search_batch(self._h, C.c_void_p(u.data_ptr()), B, T, C.c_void_p(out_ids.data_ptr()),
+                                           C.c_void_p(out_scores.data_ptr()),
+                                           C.c_void_p(out_status.data_ptr()) if out_status is not None else None,
+                                           None, ops._stream_ptr(stream)))
+        self._keep = u
+
     def search(self, users, level_topn, stream=None):
         """users: [B, user_floats] numpy (host: H2D inside the call) or CUDA tensor.
         Returns dict(ids i64[B,k], scores f32[B,k], status i32[B], n_scored[5], n_expanded[5])."""

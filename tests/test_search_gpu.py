@@ -371,12 +371,15 @@ def test_shard_group_exchange_in_library(nb, oracle, world):
     outs = [[(torch.empty((B, T[5]), dtype=torch.int64, device="cuda"), torch.empty((B, T[5]), dtype=torch.float32, device="cuda"),
               torch.empty((B,), dtype=torch.int32, device="cuda")) for _ in range(n_seq)] for _ in range(2)]
     before = nb.launch_count()
+    all_users = torch.from_numpy(world["queries"][:n_seq * B]).cuda()
+    side = torch.cuda.Stream()                  # not the legacy default stream: that one serialises with everything
+    torch.cuda.synchronize()
     for i in range(n_seq):
-        users = torch.from_numpy(world["queries"][i * B:(i + 1) * B]).cuda()
         for r in range(2):                      # both members enqueue on the same stream; nothing blocks the host
-            members[r].search(shards[r][1], users, Ts, T[5], *outs[r][i])
+            members[r].search(shards[r][1], all_users[i * B:(i + 1) * B], Ts, T[5], *outs[r][i], stream=side)
     for m in members:
         m.wait()
+    torch.cuda.synchronize()
     assert nb.launch_count() - before >= n_seq * 2 * 20
     for i in range(n_seq):
         for q in range(B):
@@ -414,10 +417,13 @@ def test_shard_group_failed_query_fails_everywhere(nb, oracle, world):
         searchers.append(nb.Searcher(ix, world["scorer"], B, Ts[r]))
     outs = [(torch.zeros((B, 40), dtype=torch.int64, device="cuda"), torch.zeros((B, 40), dtype=torch.float32, device="cuda"),
              torch.zeros((B,), dtype=torch.int32, device="cuda")) for _ in range(2)]
+    side = torch.cuda.Stream()
+    torch.cuda.synchronize()
     for r in range(2):
-        members[r].search(searchers[r], users, Ts[r], 40, *outs[r])
+        members[r].search(searchers[r], users, Ts[r], 40, *outs[r], stream=side)
     for m in members:
         m.wait()
+    torch.cuda.synchronize()
     for r in range(2):
         assert np.all(outs[r][2].cpu().numpy() == 3)
         assert np.all(outs[r][0].cpu().numpy() == -1)

@@ -57,10 +57,13 @@ def _worker(rank, world, port, out_dir):
     u_dev = torch.from_numpy(users).cuda()
     outs = [(torch.empty((B, T[5]), dtype=torch.int64, device="cuda"), torch.empty((B, T[5]), dtype=torch.float32, device="cuda"),
              torch.empty((B,), dtype=torch.int32, device="cuda")) for _ in range(n_seq)]
+    side = torch.cuda.Stream()
+    torch.cuda.synchronize()
     for rep in range(3):
         for i in range(n_seq):
-            grp.search(se, u_dev[i * B:(i + 1) * B], Ts, T[5], *outs[i])
+            grp.search(se, u_dev[i * B:(i + 1) * B], Ts, T[5], *outs[i], stream=side)
         grp.wait()
+    torch.cuda.synchronize()
     np.save(os.path.join(out_dir, f"dev_id_{rank}.npy"), np.stack([o[0].cpu().numpy() for o in outs]))
     np.save(os.path.join(out_dir, f"dev_sc_{rank}.npy"), np.stack([o[1].cpu().numpy() for o in outs]))
     dist.barrier()
