@@ -30,6 +30,10 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# one hardware work queue per stream (default 8 are shared round-robin): the shard group's merge stream holds a kernel
+# that waits for the peers' deliveries, and work of another stream queued behind it in the SAME hardware queue would
+# wait too (no deadlock across GPUs, but the search/merge overlap would be lost)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 EF_TOPN = {200: [100, 200, 200, 200, 200, 200],      # reference README.md:216
            400: [100, 200, 400, 400, 400, 200]}      # NANN_impls/nann/benchmark/gen_runmeta.py:23

@@ -331,7 +331,36 @@ void nann_shard_group_destroy(nann_shard_group_t* g);
 nann_status nann_search_sharded(nann_searcher_t* s, nann_shard_group_t* g, const float* users, int B,
                                 const int32_t level_topn_shard[6], int k_out, int64_t* out_item_ids,
                                 float* out_scores, int32_t* out_status, void* stream);
+/* The two phases of nann_search_sharded as separate calls, for ONE host thread that drives several members
+ * (shards on one GPU, or one thread per box driving all GPUs): push every member first, then merge every member.
+ * (A member's merge waits on the device for the other members' pushes; enqueueing it before those pushes exist
+ * can stall the GPU's work queues behind the waiting kernel.)  At most one push may be pending per group. */
+nann_status nann_search_sharded_push(nann_searcher_t* s, nann_shard_group_t* g, const float* users, int B,
+                                     const int32_t level_topn_shard[6], void* stream);
+nann_status nann_search_sharded_merge(nann_shard_group_t* g, int k_out, int64_t* out_item_ids, float* out_scores,
+                                      int32_t* out_status);
 nann_status nann_shard_group_wait(nann_shard_group_t* g, void* stream, int host_block);
+
+/* ------------------------------------------------------------------------------------------
+ * Index construction.  The reference builds its graph offline with faiss
+ * IndexHNSWFlat(d, M) and dumps per-level CSR files (NANN_impls/nann/delivery/build_hnsw_index.py:33-67);
+ * this builds the same FILES on the GPU: per level l < n_levels the links of the nodes whose level reaches l
+ * (levels[i] = highest level of node i, 0-based, drawn by the caller with faiss's distribution), at most 2M
+ * links at level 0 and M above, rows closest-first.  Batch construction instead of faiss's sequential
+ * insertion: exact k-NN candidates (tensor-core brute force + fp32 refinement), HNSW's diversity heuristic for
+ * the forward links, reverse links, truncation -- so the graph is a valid HNSW in the reference's layout, not
+ * faiss's graph (which no reference test pins).  dim must be 128, 2 <= M <= 32.
+ * Outputs through the allocator callback (host or device memory): 2*l = values of level l (int32 node ids),
+ * 2*l+1 = row_splits of level l (int64 [n+1]).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  double seconds_knn;        /* candidate search + refinement + heuristic, all levels */
+  double seconds_links;      /* reverse links, de-duplication, truncation */
+  int64_t n_forward_links;
+  int64_t n_overflow;        /* candidate pairs dropped because a row's append buffer was full (0 on shuffled data) */
+} nann_hnsw_build_stats_t;
+nann_status nann_hnsw_build(const float* emb, int64_t n, int dim, const int32_t* levels, int M, int n_levels,
+                            int device, nann_alloc_fn alloc, void* alloc_ctx, nann_hnsw_build_stats_t* stats);
 
 /* ------------------------------------------------------------------------------------------
  * Executor: blaze-benchmark's load generator + session pool around the search call

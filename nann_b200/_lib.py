@@ -105,6 +105,8 @@ def lib():
     L.nann_shard_group_destroy.argtypes = [vp]
     L.nann_search_sharded.argtypes = [vp, vp, vp, i32, vp, i32, vp, vp, vp, vp]
     L.nann_shard_group_wait.argtypes = [vp, vp, i32]
+    L.nann_search_sharded_push.argtypes = [vp, vp, vp, i32, vp, vp]
+    L.nann_search_sharded_merge.argtypes = [vp, i32, vp, vp, vp]
     L.nann_eval_searcher_create.argtypes = [vp, vp, i32, vp, i32, vp]
     L.nann_eval_searcher_destroy.restype = None
     L.nann_eval_searcher_destroy.argtypes = [vp]

@@ -24,6 +24,8 @@ struct nann_shard_group {
   unsigned int* counters = nullptr;                // [0] push CTAs, [1] merge CTAs
   int* error = nullptr;                            // device flag: a wait timed out
   unsigned long long seq = 0;
+  bool pending = false;                            // a push whose merge has not been enqueued yet
+  int pend_B = 0, pend_k = 0;
   cudaStream_t merge_stream = nullptr;
   cudaEvent_t ev_push = nullptr, ev_merged = nullptr;
   // device staging for host outputs
@@ -155,25 +157,23 @@ nann_status nann_shard_group_connect_local(nann_shard_group_t* const* members, i
   return NANN_OK;
 }
 
-nann_status nann_search_sharded(nann_searcher_t* s, nann_shard_group_t* g, const float* users, int B,
-                                const int32_t T[6], int k_out, int64_t* out_item_ids, float* out_scores,
-                                int32_t* out_status, void* stream) {
+// phase 1: this shard's search on `stream`, its records pushed into every rank's window by the final top-k kernel
+nann_status nann_search_sharded_push(nann_searcher_t* s, nann_shard_group_t* g, const float* users, int B,
+                                     const int32_t T[6], void* stream) {
   NANN_TRY(require_device());
   if (!g) return fail(NANN_INVALID_ARGUMENT, "null shard group");
   NANN_TRY(search_check_args(s, users, B, T));
   if (!g->connected) return fail(NANN_FAILED_PRECONDITION, "shard group is not connected (nann_shard_group_connect)");
+  if (g->pending) return fail(NANN_FAILED_PRECONDITION, "a pushed search is waiting for nann_search_sharded_merge");
   if (s->ix->device != g->device) return fail(NANN_INVALID_ARGUMENT, "searcher is on device %d, shard group on %d", s->ix->device, g->device);
   const int k_s = T[5];
   if (B > g->max_batch || k_s > g->max_k) return fail(NANN_INVALID_ARGUMENT, "batch %d / k %d exceed the group's window (%d / %d)", B, k_s, g->max_batch, g->max_k);
-  if (k_out < 0 || (int64_t)g->world * k_s < k_out)   // TopKV2 on the concatenation: topk_op.cc:66-69
-    return fail(NANN_INVALID_ARGUMENT, "input must have at least k columns. Had %lld, needed %d", (long long)g->world * k_s, k_out);
   if (B == 0) return NANN_OK;          // every rank sees the same B, so every rank skips the sequence
   cudaStream_t st = (cudaStream_t)stream;
   NANN_CUDA(cudaSetDevice(g->device));
-  const unsigned long long seq = g->seq++;
+  const unsigned long long seq = g->seq;
   const int slot = (int)(seq % (unsigned)g->depth);
   const size_t slot_off = SHARD_FLAG_BYTES + (size_t)slot * g->slot_bytes;
-
   ShardPush P{};
   P.world = g->world; P.rank = g->rank; P.k = k_s; P.B = B;
   for (int p = 0; p < g->world; ++p) {
@@ -186,8 +186,25 @@ nann_status nann_search_sharded(nann_searcher_t* s, nann_shard_group_t* g, const
   P.counter = g->counters + 0; P.error = g->error;
   NANN_TRY(search_enqueue(s, users, B, T, st, &P));
   NANN_CUDA(cudaEventRecord(g->ev_push, st));
+  g->seq = seq + 1;
+  g->pending = true; g->pend_B = B; g->pend_k = k_s;
+  return NANN_OK;
+}
 
-  // ---- exchange wait + merge on the group's stream: the caller's stream is free for the next batch
+// phase 2, on the group's stream (the caller's stream is free for the next batch): wait for every shard's delivery,
+// merge, tell the peers the slot is free
+nann_status nann_search_sharded_merge(nann_shard_group_t* g, int k_out, int64_t* out_item_ids, float* out_scores,
+                                      int32_t* out_status) {
+  NANN_TRY(require_device());
+  if (!g) return fail(NANN_INVALID_ARGUMENT, "null shard group");
+  if (!g->pending) return NANN_OK;     // B == 0 push, or nothing pushed
+  const int B = g->pend_B, k_s = g->pend_k;
+  if (k_out < 0 || (int64_t)g->world * k_s < k_out)   // TopKV2 on the concatenation: topk_op.cc:66-69
+    return fail(NANN_INVALID_ARGUMENT, "input must have at least k columns. Had %lld, needed %d", (long long)g->world * k_s, k_out);
+  NANN_CUDA(cudaSetDevice(g->device));
+  const unsigned long long seq = g->seq - 1;
+  const int slot = (int)(seq % (unsigned)g->depth);
+  const size_t slot_off = SHARD_FLAG_BYTES + (size_t)slot * g->slot_bytes;
   const bool host_out = (out_item_ids && !is_device_ptr(out_item_ids)) || (out_scores && !is_device_ptr(out_scores)) ||
                         (out_status && !is_device_ptr(out_status));
   const bool need_stage = host_out || !out_item_ids || !out_scores || !out_status;
@@ -201,6 +218,7 @@ nann_status nann_search_sharded(nann_searcher_t* s, nann_shard_group_t* g, const
     g->o_k = std::max(k_out, 1);
   }
   cudaStream_t ms = g->merge_stream;
+  g->pending = false;
   NANN_CUDA(cudaStreamWaitEvent(ms, g->ev_push, 0));
   NANN_LAUNCH(shard_wait_kernel, 1, 32, 0, ms, shard_arrive(g->window, slot, 0), g->world, seq, g->error);
   ShardMergeArgs M{};
@@ -228,6 +246,15 @@ nann_status nann_search_sharded(nann_searcher_t* s, nann_shard_group_t* g, const
     if (err) return fail(NANN_DEADLINE_EXCEEDED, "shard exchange timed out: a peer did not deliver (ranks out of step, or a rank died)");
   }
   return NANN_OK;
+}
+
+nann_status nann_search_sharded(nann_searcher_t* s, nann_shard_group_t* g, const float* users, int B,
+                                const int32_t T[6], int k_out, int64_t* out_item_ids, float* out_scores,
+                                int32_t* out_status, void* stream) {
+  if (g && T && (k_out < 0 || (int64_t)g->world * T[5] < k_out))
+    return fail(NANN_INVALID_ARGUMENT, "input must have at least k columns. Had %lld, needed %d", (long long)g->world * T[5], k_out);
+  NANN_TRY(nann_search_sharded_push(s, g, users, B, T, stream));
+  return nann_search_sharded_merge(g, k_out, out_item_ids, out_scores, out_status);
 }
 
 nann_status nann_shard_group_wait(nann_shard_group_t* g, void* stream, int host_block) {

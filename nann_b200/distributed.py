@@ -164,6 +164,23 @@ class ShardGroup:
         self._keep = u
         return out_scores, out_ids, out_status
 
+    def push(self, searcher, users, level_topn_shard, stream=None):
+        """phase 1 only (one host thread driving several members: push all of them, then merge all of them)"""
+        from . import ops
+        uf = searcher.scorer.user_floats
+        if not (ops._is_torch(users) and users.is_cuda):
+            raise TypeError("push: users must be a CUDA tensor")
+        u = users.contiguous().float().reshape(-1, uf)
+        T = (C.c_int32 * 6)(*[int(t) for t in level_topn_shard])
+        self._lib.check(self._lib.lib().nann_search_sharded_push(searcher._h, self._h, C.c_void_p(u.data_ptr()), u.shape[0], T,
+                                                                 ops._stream_ptr(stream)))
+        self._keep = u
+
+    def merge(self, k_out, out_ids, out_scores, out_status):
+        """phase 2 of the pending push: CUDA output tensors, enqueue only (see wait())"""
+        self._lib.check(self._lib.lib().nann_search_sharded_merge(self._h, int(k_out), C.c_void_p(out_ids.data_ptr()),
+                                                                  C.c_void_p(out_scores.data_ptr()), C.c_void_p(out_status.data_ptr())))
+
     def wait(self, stream=None, host_block=True):
         from . import ops
         self._lib.check(self._lib.lib().nann_shard_group_wait(self._h, ops._stream_ptr(stream), int(bool(host_block))))

@@ -909,3 +909,136 @@ out:
   fclose(f);
   return st;
 }
+
+
+/* ============================================================================================
+ * Index construction.  NOT a restatement of faiss: the reference builds its graph with
+ * faiss IndexHNSWFlat(d, 32) (NANN_impls/nann/delivery/build_hnsw_index.py:33-36), a third-party
+ * library that is absent here and whose sequential-insertion graph no reference test pins.  This is
+ * the CPU statement of the batch construction the CUDA builder implements (builder_kernels.cuh), so
+ * that the GPU files can be compared bit for bit:
+ *   d2(i,j)   = (sq_i + sq_j) - 2 * dot(i,j), dot and sq sequential fmaf chains over k = 0..d-1
+ *   candidates of i = the n_cand members closest to i by (d2, id), i excluded
+ *   forward links   = HNSW's diversity heuristic over the candidates in that order: keep j unless an
+ *                     already kept m has d2(j,m) < d2(i,j); stop at M links
+ *   links of i      = forward(i) U {j : i in forward(j)}, one entry per neighbour, the `cap` closest
+ *                     by (d2, id), closest first.
+ * parity unpinned by the reference (see header); pinned against the torch builder nann_b200/index.py by edge overlap.
+ * ============================================================================================ */
+static float dot_seq(const float* a, const float* b, int d) {
+  float acc = 0.f;
+  for (int k = 0; k < d; ++k) acc = fmaf(a[k], b[k], acc);
+  return acc;
+}
+static uint32_t okey(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u << 1) == 0) u = 0;
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+static int cmp_u64(const void* a, const void* b) {
+  uint64_t x = *(const uint64_t*)a, y = *(const uint64_t*)b;
+  return x < y ? -1 : (x > y ? 1 : 0);
+}
+typedef struct { const float* X; const float* sq; int64_t s; int d, n_cand, M; int32_t* fwd; float* fwd_d; int32_t* fwd_cnt; int64_t next; pthread_mutex_t mu; } build_job_t;
+
+static void build_forward_row(build_job_t* J, int64_t i, uint64_t* keys, float* dist) {
+  const int d = J->d;
+  const float* xi = J->X + i * d;
+  int64_t n = 0;
+  for (int64_t j = 0; j < J->s; ++j) {
+    if (j == i) continue;
+    const float d2 = (J->sq[i] + J->sq[j]) - 2.0f * dot_seq(xi, J->X + j * d, d);
+    keys[n++] = ((uint64_t)okey(d2) << 32) | (uint32_t)j;
+    (void)dist;
+  }
+  qsort(keys, (size_t)n, sizeof(uint64_t), cmp_u64);
+  const int c = (int)(n < J->n_cand ? n : J->n_cand);
+  int nk = 0;
+  int32_t kept[64];
+  for (int a = 0; a < c && nk < J->M; ++a) {
+    const int32_t j = (int32_t)(uint32_t)keys[a];
+    const uint32_t ok = (uint32_t)(keys[a] >> 32);
+    const uint32_t fb = (ok & 0x80000000u) ? (ok & 0x7fffffffu) : ~ok;
+    float dj;
+    memcpy(&dj, &fb, 4);
+    int blocked = 0;
+    for (int t = 0; t < nk && !blocked; ++t) {
+      const int32_t m = kept[t];
+      const float pd = (J->sq[j] + J->sq[m]) - 2.0f * dot_seq(J->X + (int64_t)j * d, J->X + (int64_t)m * d, d);
+      if (pd < dj) blocked = 1;
+    }
+    if (!blocked) {
+      kept[nk] = j;
+      J->fwd[i * J->M + nk] = j;
+      J->fwd_d[i * J->M + nk] = dj;
+      ++nk;
+    }
+  }
+  J->fwd_cnt[i] = nk;
+}
+static void* build_worker(void* arg) {
+  build_job_t* J = (build_job_t*)arg;
+  uint64_t* keys = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)(J->s > 0 ? J->s : 1));
+  for (;;) {
+    pthread_mutex_lock(&J->mu);
+    const int64_t i = J->next++;
+    pthread_mutex_unlock(&J->mu);
+    if (i >= J->s) break;
+    build_forward_row(J, i, keys, NULL);
+  }
+  free(keys);
+  return NULL;
+}
+
+/* X [s][d] members of one level; out_links [s][cap] (member-local ids), out_cnt [s] */
+int orc_build_level(const float* X, int64_t s, int d, int n_cand, int M, int cap, int nthreads,
+                    int32_t* out_links, int32_t* out_cnt) {
+  if (s < 0 || d <= 0 || M <= 0 || M > 64 || cap <= 0 || n_cand < 0) return ORC_INVALID_ARGUMENT;
+  if (s == 0) return ORC_OK;
+  float* sq = (float*)malloc(sizeof(float) * (size_t)s);
+  for (int64_t i = 0; i < s; ++i) sq[i] = dot_seq(X + i * d, X + i * d, d);
+  build_job_t J;
+  J.X = X; J.sq = sq; J.s = s; J.d = d; J.n_cand = n_cand; J.M = M; J.next = 0;
+  J.fwd = (int32_t*)malloc(sizeof(int32_t) * (size_t)(s * M));
+  J.fwd_d = (float*)malloc(sizeof(float) * (size_t)(s * M));
+  J.fwd_cnt = (int32_t*)calloc((size_t)s, sizeof(int32_t));
+  pthread_mutex_init(&J.mu, NULL);
+  if (nthreads < 1) nthreads = 1;
+  pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)nthreads);
+  for (int t = 1; t < nthreads; ++t) pthread_create(&th[t], NULL, build_worker, &J);
+  build_worker(&J);
+  for (int t = 1; t < nthreads; ++t) pthread_join(th[t], NULL);
+  free(th);
+  pthread_mutex_destroy(&J.mu);
+  /* reverse links */
+  int64_t* rev_off = (int64_t*)calloc((size_t)s + 1, sizeof(int64_t));
+  for (int64_t i = 0; i < s; ++i)
+    for (int e = 0; e < J.fwd_cnt[i]; ++e) rev_off[J.fwd[i * M + e] + 1]++;
+  for (int64_t i = 0; i < s; ++i) rev_off[i + 1] += rev_off[i];
+  uint64_t* rev = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)(rev_off[s] > 0 ? rev_off[s] : 1));
+  int64_t* fill = (int64_t*)calloc((size_t)s, sizeof(int64_t));
+  for (int64_t i = 0; i < s; ++i)
+    for (int e = 0; e < J.fwd_cnt[i]; ++e) {
+      const int32_t j = J.fwd[i * M + e];
+      rev[rev_off[j] + fill[j]++] = ((uint64_t)okey(J.fwd_d[i * M + e]) << 32) | (uint32_t)i;
+    }
+  int64_t max_list = M;
+  for (int64_t i = 0; i < s; ++i) if (M + rev_off[i + 1] - rev_off[i] > max_list) max_list = M + rev_off[i + 1] - rev_off[i];
+  uint64_t* list = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)max_list);
+  for (int64_t i = 0; i < s; ++i) {
+    int64_t n = 0;
+    for (int e = 0; e < J.fwd_cnt[i]; ++e) list[n++] = ((uint64_t)okey(J.fwd_d[i * M + e]) << 32) | (uint32_t)J.fwd[i * M + e];
+    for (int64_t e = rev_off[i]; e < rev_off[i + 1]; ++e) list[n++] = rev[e];
+    qsort(list, (size_t)n, sizeof(uint64_t), cmp_u64);
+    int out = 0;
+    for (int64_t e = 0; e < n && out < cap; ++e) {
+      if (e > 0 && list[e] == list[e - 1]) continue;      /* forward and reverse entry of the same neighbour */
+      out_links[i * cap + out++] = (int32_t)(uint32_t)list[e];
+    }
+    out_cnt[i] = out;
+  }
+  free(list); free(fill); free(rev); free(rev_off);
+  free(J.fwd); free(J.fwd_d); free(J.fwd_cnt); free(sq);
+  return ORC_OK;
+}

@@ -171,6 +171,11 @@ double orc_search_batch_mlp(const orc_index_t* ix, const orc_mlp_t* m, const flo
 int orc_huge_const_load(const char* path, int dtype, const int64_t* shape, int rank,
                         void* dst, int64_t dst_bytes);
 
+/* ---- index construction: CPU statement of the CUDA builder's batch construction (NOT faiss; see the .c file).
+ * X [s][d] = the members of one level; out_links [s][cap] member-local ids closest-first, out_cnt [s]. */
+int orc_build_level(const float* X, int64_t s, int d, int n_cand, int M, int cap, int nthreads,
+                    int32_t* out_links, int32_t* out_cnt);
+
 const char* orc_version(void);
 
 #ifdef __cplusplus

@@ -297,3 +297,36 @@ class Index:
         secs = lib().orc_search_batch_mlp(C.byref(self.c), C.c_void_p(mlp.h), _p(users), C.c_int64(B), _p(T),
                                           C.c_int(nthreads), _p(ids), _p(sc), _p(status), C.byref(tot))
         return dict(ids=ids, scores=sc, status=status, seconds=secs, n_scored=tot.value)
+
+
+def build_hnsw(emb, levels, M=32, n_levels=2, nthreads=0):
+    """CPU statement of the CUDA index builder (nann_hnsw_build): -> (values [l] i32, row_splits [l] i64 [n+1]).
+    levels[i] = highest level of node i (0-based)."""
+    emb = _c(emb, np.float32)
+    n, d = emb.shape
+    levels = np.asarray(levels)
+    nthreads = nthreads or min(os.cpu_count() or 1, 32)
+    values, row_splits = [], []
+    for l in range(n_levels):
+        nodes = np.nonzero(levels >= l)[0].astype(np.int64)
+        s = len(nodes)
+        cap = 2 * M if l == 0 else M
+        counts = np.zeros(n, np.int64)
+        rows = {}
+        if s >= 2:
+            X = _c(emb[nodes], np.float32)
+            links = np.zeros((s, cap), np.int32)
+            cnt = np.zeros(s, np.int32)
+            st = lib().orc_build_level(_p(X), C.c_int64(s), int(d), int(min(cap + M, s - 1)), int(M), int(cap), int(nthreads),
+                                       _p(links), _p(cnt))
+            if st != OK:
+                raise OracleError(st, "orc_build_level")
+            counts[nodes] = cnt
+            vals = np.concatenate([nodes[links[i, :cnt[i]]] for i in range(s)]) if cnt.sum() else np.zeros(0, np.int64)
+        else:
+            vals = np.zeros(0, np.int64)
+        rs = np.zeros(n + 1, np.int64)
+        rs[1:] = np.cumsum(counts)
+        values.append(vals.astype(np.int32))
+        row_splits.append(rs)
+    return values, row_splits

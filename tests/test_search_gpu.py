@@ -375,8 +375,10 @@ def test_shard_group_exchange_in_library(nb, oracle, world):
     side = torch.cuda.Stream()                  # not the legacy default stream: that one serialises with everything
     torch.cuda.synchronize()
     for i in range(n_seq):
-        for r in range(2):                      # both members enqueue on the same stream; nothing blocks the host
-            members[r].search(shards[r][1], all_users[i * B:(i + 1) * B], Ts, T[5], *outs[r][i], stream=side)
+        for r in range(2):                      # one host thread drives both members: push both, then merge both
+            members[r].push(shards[r][1], all_users[i * B:(i + 1) * B], Ts, stream=side)
+        for r in range(2):
+            members[r].merge(T[5], *outs[r][i])
     for m in members:
         m.wait()
     torch.cuda.synchronize()
@@ -420,7 +422,9 @@ def test_shard_group_failed_query_fails_everywhere(nb, oracle, world):
     side = torch.cuda.Stream()
     torch.cuda.synchronize()
     for r in range(2):
-        members[r].search(searchers[r], users, Ts[r], 40, *outs[r], stream=side)
+        members[r].push(searchers[r], users, Ts[r], stream=side)
+    for r in range(2):
+        members[r].merge(40, *outs[r])
     for m in members:
         m.wait()
     torch.cuda.synchronize()
