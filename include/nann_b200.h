@@ -172,6 +172,21 @@ NANN_RAGGED_DECL(int32_t, i32)
 NANN_RAGGED_DECL(int64_t, i64)
 #undef NANN_RAGGED_DECL
 
+/* BloomFilterDifference (UO/bitmap_op/bitmap_ops.cc:264-432): BitmapRefDifference with a 4-hash Bloom filter over
+ * idx_flag (int32[n_flags], n_flags >= bucket_size; Ref input, mutated in place) instead of an exact bitmap: a value is
+ * emitted when at least one of its four bits (Fingerprint64 of the decimal string, optional `% bucket`, the four
+ * prime-modulus hashes of :340-351) was still clear; all four are set afterwards.  Values are processed in order over
+ * all groups, like the reference's loop.  outputs 0 = c_values (T), 1 = c_row_splits (i64).  InvalidArgument for an
+ * invalid ragged input (code 1|2|3) and for n_flags < bucket_size (the reference writes out of bounds). */
+nann_status nann_bloom_filter_difference_i32(const int32_t* idx_next_values, int64_t n_values,
+                                             const int64_t* idx_next_row_splits, int64_t n_row_splits, int32_t* idx_flag,
+                                             int64_t n_flags, int64_t bucket, int64_t bucket_size, nann_alloc_fn alloc,
+                                             void* alloc_ctx, void* stream);
+nann_status nann_bloom_filter_difference_i64(const int64_t* idx_next_values, int64_t n_values,
+                                             const int64_t* idx_next_row_splits, int64_t n_row_splits, int32_t* idx_flag,
+                                             int64_t n_flags, int64_t bucket, int64_t bucket_size, nann_alloc_fn alloc,
+                                             void* alloc_ctx, void* stream);
+
 /* GatherV2 on axis 0: out[i] = table[ids[i]], row_bytes per row (build_opt_graph.py:92,144).
  * InvalidArgument when an id is outside [0, n_rows). */
 nann_status nann_gather_rows(const void* table, int64_t n_rows, int64_t row_bytes,

@@ -9,10 +9,10 @@ _lib.lib()  # raise ImportError now rather than at first use
 
 from ._lib import NannError, SCORER_EXACT, SCORER_TENSOR, launch_count, device_info  # noqa: E402
 from . import ops  # noqa: E402
-from .ops import (group_gather, bitmap_ref_difference, top_k, batch_top_k_on_rt, gather, huge_const, HugeConst,  # noqa: E402
+from .ops import (group_gather, bitmap_ref_difference, bloom_filter_difference, top_k, batch_top_k_on_rt, gather, huge_const, HugeConst,  # noqa: E402
                   Scorer, blaze_xla_op, score_ids, merge_topk)
 from .retrieval import Index, Searcher, EvalSearcher, retrieve_opwise  # noqa: E402
 
 __all__ = ["NannError", "SCORER_EXACT", "SCORER_TENSOR", "launch_count", "device_info", "ops",
-           "group_gather", "bitmap_ref_difference", "top_k", "batch_top_k_on_rt", "gather", "huge_const", "HugeConst",
+           "group_gather", "bitmap_ref_difference", "bloom_filter_difference", "top_k", "batch_top_k_on_rt", "gather", "huge_const", "HugeConst",
            "Scorer", "blaze_xla_op", "score_ids", "merge_topk", "Index", "Searcher", "EvalSearcher", "retrieve_opwise"]

@@ -64,6 +64,8 @@ def lib():
         getattr(L, f).argtypes = [vp, i64, vp, i64, vp, i64, vp, i64, i32, ALLOC_FN, vp, vp]
     for f in ("nann_bitmap_ref_difference_i32", "nann_bitmap_ref_difference_i64"):
         getattr(L, f).argtypes = [vp, i64, vp, i64, vp, i64, ALLOC_FN, vp, vp]
+    for f in ("nann_bloom_filter_difference_i32", "nann_bloom_filter_difference_i64"):
+        getattr(L, f).argtypes = [vp, i64, vp, i64, vp, i64, i64, i64, ALLOC_FN, vp, vp]
     L.nann_topk_v2_f32.argtypes = [vp, i64, i64, C.c_int32, i32, vp, vp, vp]
     L.nann_gather_rows.argtypes = [vp, i64, i64, vp, i64, vp, vp]
     L.nann_scorer_create_mlp.argtypes = [i32, i32, vp, vp, vp, vp, vp, i32, vp]

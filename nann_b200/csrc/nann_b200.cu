@@ -20,5 +20,6 @@
 #include "lib_shard.inl"
 #include "builder_kernels.cuh"
 #include "lib_builder.inl"
+#include "lib_bloom.inl"
 #include "lib_eval.inl"
 #include "lib_executor.inl"

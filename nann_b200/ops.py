@@ -97,6 +97,28 @@ def bitmap_ref_difference(idx_next_values, idx_next_row_splits, idx_flag, stream
     return out.arrays.get(0, np.empty(0, dt)), out.arrays[1], idx_flag
 
 
+def bloom_filter_difference(idx_next_values, idx_next_row_splits, idx_flag, bucket=0, bucket_size=1, stream=None):
+    """tf.bloom_filter_difference (bitmap_ops.cc:264-289): BitmapRefDifference with a 4-hash Bloom filter over idx_flag
+    (int32 numpy array or CUDA tensor with at least bucket_size words; mutated in place, returned as third output)."""
+    dt = np.dtype(idx_next_values.dtype if not _is_torch(idx_next_values) else str(idx_next_values.dtype).split(".")[-1])
+    if dt not in (np.dtype("int32"), np.dtype("int64")):
+        raise TypeError("BloomFilterDifference: T must be int32 or int64")
+    if _is_torch(idx_flag):
+        fl_ptr, n_fl, keep = _as(idx_flag, np.int32)
+        if keep is not idx_flag and keep.data_ptr() != idx_flag.data_ptr():
+            raise TypeError("idx_flag must be a contiguous int32 tensor (it is mutated in place)")
+    else:
+        if idx_flag.dtype != np.int32 or not idx_flag.flags["C_CONTIGUOUS"] or not idx_flag.flags["WRITEABLE"]:
+            raise TypeError("idx_flag must be a writable contiguous int32 array (it is mutated in place)")
+        fl_ptr, n_fl = C.c_void_p(idx_flag.ctypes.data), idx_flag.size
+    v, n_v, k0 = _as(idx_next_values, dt)
+    rs, n_rs, k1 = _as(idx_next_row_splits, np.int64)
+    out = _Outputs({0: dt, 1: np.int64})
+    fn = (_lib.lib().nann_bloom_filter_difference_i32 if dt == np.int32 else _lib.lib().nann_bloom_filter_difference_i64)
+    check(fn(v, n_v, rs, n_rs, fl_ptr, n_fl, int(bucket), int(bucket_size), out.fn, None, _stream_ptr(stream)))
+    return out.arrays.get(0, np.empty(0, dt)), out.arrays[1], idx_flag
+
+
 def top_k(input, k, sorted=True, stream=None):  # noqa: A002 - tf.math.top_k's argument names
     """tf.math.top_k / TopKV2 on the last axis (topk_op.cc).  Returns (values f32, indices i32)."""
     if _is_torch(input):

@@ -1042,3 +1042,108 @@ int orc_build_level(const float* X, int64_t s, int d, int n_cand, int M, int cap
   free(J.fwd); free(J.fwd_d); free(J.fwd_cnt); free(sq);
   return ORC_OK;
 }
+
+
+/* ============================================================================================
+ * BloomFilterDifference  (UO/bitmap_op/bitmap_ops.cc:264-432)
+ * Fingerprint64 = farmhash::Fingerprint64 (tensorflow/core/platform/fingerprint.h:80-90), a third-party
+ * dependency that is not vendored in the reference tree (tensorflow/workspace.bzl:250-257 pins
+ * google/farmhash @ 816a4ae622e964763ca0862d9dbd19324a1eaf45).  Restated below from the published
+ * algorithm (farmhashna::Hash64, inputs up to 32 bytes -- decimal strings of int64 have at most 20) and
+ * pinned against the vectors the reference's own tests hold:
+ *   tensorflow/python/kernel_tests/string_to_hash_bucket_op_test.py:46-49  ('a','b','c','d')
+ *   tensorflow/core/platform/fingerprint_test.cc:27-28                     ("Hello","World")
+ * (both exercise the 1..3 and 4..7 byte branches; the 8..16 and 17..32 byte branches follow the published
+ * source with no reference-held vector).
+ * ============================================================================================ */
+#define FH_K0 0xc3a5c85c97cb3127ULL
+#define FH_K1 0xb492b66fbe98f273ULL
+#define FH_K2 0x9ae16a3b2f90404fULL
+static uint64_t fh_fetch64(const char* p) { uint64_t v; memcpy(&v, p, 8); return v; }
+static uint32_t fh_fetch32(const char* p) { uint32_t v; memcpy(&v, p, 4); return v; }
+static uint64_t fh_rot(uint64_t v, int s) { return s == 0 ? v : ((v >> s) | (v << (64 - s))); }
+static uint64_t fh_shift_mix(uint64_t v) { return v ^ (v >> 47); }
+static uint64_t fh_len16(uint64_t u, uint64_t v, uint64_t mul) {
+  uint64_t a = (u ^ v) * mul;
+  a ^= (a >> 47);
+  uint64_t b = (v ^ a) * mul;
+  b ^= (b >> 47);
+  return b * mul;
+}
+uint64_t orc_fingerprint64(const char* s, int64_t len) {
+  if (len <= 16) {
+    if (len >= 8) {
+      const uint64_t mul = FH_K2 + (uint64_t)len * 2, a = fh_fetch64(s) + FH_K2, b = fh_fetch64(s + len - 8);
+      const uint64_t c = fh_rot(b, 37) * mul + a, d = (fh_rot(a, 25) + b) * mul;
+      return fh_len16(c, d, mul);
+    }
+    if (len >= 4) {
+      const uint64_t mul = FH_K2 + (uint64_t)len * 2, a = fh_fetch32(s);
+      return fh_len16((uint64_t)len + (a << 3), fh_fetch32(s + len - 4), mul);
+    }
+    if (len > 0) {
+      const uint8_t a = (uint8_t)s[0], b = (uint8_t)s[len >> 1], c = (uint8_t)s[len - 1];
+      const uint32_t y = (uint32_t)a + ((uint32_t)b << 8), z = (uint32_t)len + ((uint32_t)c << 2);
+      return fh_shift_mix(y * FH_K2 ^ z * FH_K0) * FH_K2;
+    }
+    return FH_K2;
+  }
+  if (len <= 32) {
+    const uint64_t mul = FH_K2 + (uint64_t)len * 2, a = fh_fetch64(s) * FH_K1, b = fh_fetch64(s + 8);
+    const uint64_t c = fh_fetch64(s + len - 8) * mul, d = fh_fetch64(s + len - 16) * FH_K2;
+    return fh_len16(fh_rot(a + b, 43) + fh_rot(c, 30) + d, a + fh_rot(b + FH_K2, 18) + c, mul);
+  }
+  return 0;   /* longer inputs never occur for decimal integers */
+}
+
+static int bloom_is_prime(int64_t x) {                       /* bitmap_ops.cc:395-402 ("not fit when x equal 1") */
+  for (int64_t i = (int64_t)(sqrt((double)x) + 1e-6); i > 1; i--)
+    if ((x % i) == 0) return 0;
+  return 1;
+}
+void orc_bloom_primes(int64_t bucket_size, int64_t primes[4]) {   /* :404-421 */
+  static const int mod_param[4] = {29, 47, 67, 83};
+  for (int i = 0; i < 4; i++) {
+    int64_t target = (int64_t)mod_param[i] * bucket_size * 32, p = 0;
+    for (int64_t n = target; n > 0; n--) if (bloom_is_prime(n)) { p = n; break; }
+    primes[i] = p;
+  }
+}
+/* the Differ loop (:334-359) for one node; returns `miss` */
+static int bloom_touch(int64_t node, int64_t bucket, int64_t bucket_size, const int64_t primes[4], int32_t* flags) {
+  static const int mult[4] = {1, 3, 5, 7};
+  char buf[32];
+  const int len = snprintf(buf, sizeof(buf), "%lld", (long long)node);      /* std::to_string(node) */
+  uint64_t raw = orc_fingerprint64(buf, len);
+  if (bucket > 0) raw = raw % (uint64_t)bucket;
+  int miss = 0;
+  for (int l = 0; l < 4; l++) {
+    const uint64_t lp = (uint64_t)primes[l];
+    const uint64_t tmp = ((raw * (uint64_t)mult[l]) % lp + lp) % lp;
+    const int64_t bucket_id = (int64_t)(tmp % (uint64_t)(bucket_size * 32));
+    const int fi = (int)(bucket_id >> 5), bi = (int)(bucket_id & 31);
+    if (!((uint32_t)flags[fi] & (1u << bi))) { miss++; flags[fi] = (int32_t)((uint32_t)flags[fi] | (1u << bi)); }
+  }
+  return miss;
+}
+#define ORC_BLOOM(T, SFX)                                                                                          \
+  int orc_bloom_filter_difference_##SFX(const T* v, int64_t n_v, const int64_t* rs, int64_t n_rs, int32_t* flags,  \
+                                        int64_t n_flags, int64_t bucket, int64_t bucket_size, T* c_values,          \
+                                        int64_t* c_row_splits, int64_t* n_c, int* code) {                           \
+    *code = orc_validate_ragged(n_v, rs, n_rs);                                                                     \
+    if (*code) return ORC_INVALID_ARGUMENT;                                                                         \
+    if (bucket_size < 1 || bucket < 0 || n_flags < bucket_size) return ORC_INVALID_ARGUMENT;                        \
+    *n_c = 0;                                                                                                       \
+    if (n_rs == 1) { c_row_splits[0] = 0; return ORC_OK; }                       /* void input, :312-322 */         \
+    int64_t primes[4];                                                                                              \
+    orc_bloom_primes(bucket_size, primes);                                                                          \
+    c_row_splits[0] = 0;                                                                                            \
+    for (int64_t g = 0; g + 1 < n_rs; ++g) {                                                                        \
+      for (int64_t j = rs[g]; j < rs[g + 1]; ++j)                                                                   \
+        if (bloom_touch((int64_t)v[j], bucket, bucket_size, primes, flags) > 0) c_values[(*n_c)++] = v[j];           \
+      c_row_splits[g + 1] = *n_c;                                                                                   \
+    }                                                                                                               \
+    return ORC_OK;                                                                                                  \
+  }
+ORC_BLOOM(int32_t, i32)
+ORC_BLOOM(int64_t, i64)

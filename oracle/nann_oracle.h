@@ -171,6 +171,17 @@ double orc_search_batch_mlp(const orc_index_t* ix, const orc_mlp_t* m, const flo
 int orc_huge_const_load(const char* path, int dtype, const int64_t* shape, int rank,
                         void* dst, int64_t dst_bytes);
 
+/* ---- BloomFilterDifference: UO/bitmap_op/bitmap_ops.cc:264-432.  flags (int32[n_flags], n_flags >= bucket_size) is the
+ * Ref input, mutated in place; c_values needs n_v slots, c_row_splits n_rs.  `code` = ValidateRaggedTensor result. */
+uint64_t orc_fingerprint64(const char* s, int64_t len);       /* farmhash::Fingerprint64 for len <= 32 */
+void orc_bloom_primes(int64_t bucket_size, int64_t primes[4]);
+int orc_bloom_filter_difference_i32(const int32_t* v, int64_t n_v, const int64_t* rs, int64_t n_rs, int32_t* flags,
+                                    int64_t n_flags, int64_t bucket, int64_t bucket_size, int32_t* c_values,
+                                    int64_t* c_row_splits, int64_t* n_c, int* code);
+int orc_bloom_filter_difference_i64(const int64_t* v, int64_t n_v, const int64_t* rs, int64_t n_rs, int32_t* flags,
+                                    int64_t n_flags, int64_t bucket, int64_t bucket_size, int64_t* c_values,
+                                    int64_t* c_row_splits, int64_t* n_c, int* code);
+
 /* ---- index construction: CPU statement of the CUDA builder's batch construction (NOT faiss; see the .c file).
  * X [s][d] = the members of one level; out_links [s][cap] member-local ids closest-first, out_cnt [s]. */
 int orc_build_level(const float* X, int64_t s, int d, int n_cand, int M, int cap, int nthreads,

@@ -330,3 +330,28 @@ def build_hnsw(emb, levels, M=32, n_levels=2, nthreads=0):
         values.append(vals.astype(np.int32))
         row_splits.append(rs)
     return values, row_splits
+
+
+def fingerprint64(b):
+    """farmhash::Fingerprint64 (inputs up to 32 bytes)"""
+    lib().orc_fingerprint64.restype = C.c_uint64
+    b = bytes(b)
+    return int(lib().orc_fingerprint64(C.c_char_p(b), C.c_int64(len(b))))
+
+
+def bloom_filter_difference(idx_next_values, idx_next_row_splits, idx_flag, bucket=0, bucket_size=1):
+    """Mirrors tf.bloom_filter_difference (BloomFilterDifference op); idx_flag (int32 array) is mutated in place.
+    Returns (c_values, c_row_splits, idx_flag)."""
+    v = np.ascontiguousarray(idx_next_values)
+    assert v.dtype in (np.int32, np.int64)
+    rs = _c(idx_next_row_splits, np.int64)
+    assert idx_flag.dtype == np.int32 and idx_flag.flags["C_CONTIGUOUS"]
+    out = np.empty(max(v.size, 1), v.dtype)
+    ors = np.empty(max(rs.size, 1), np.int64)
+    n_c, code = C.c_int64(0), C.c_int(0)
+    fn = lib().orc_bloom_filter_difference_i32 if v.dtype == np.int32 else lib().orc_bloom_filter_difference_i64
+    st = fn(_p(v), C.c_int64(v.size), _p(rs), C.c_int64(rs.size), _p(idx_flag), C.c_int64(idx_flag.size), C.c_int64(bucket),
+            C.c_int64(bucket_size), _p(out), _p(ors), C.byref(n_c), C.byref(code))
+    if st != OK:
+        raise OracleError(st, f"Invalid RaggedTensor input0 a, code: {code.value}" if code.value else "bad bloom arguments")
+    return out[:n_c.value].copy(), ors[:rs.size].copy(), idx_flag

@@ -127,6 +127,32 @@ kat = {
     "splits_gather": {"source": "UO/beam_search_op/splits_gather_test.py:7-10,18-24", "kind": "stated in reference docstring",
         "splits": [0, 2, 5, 7, 10], "indices_values": [0, 1, 3], "indices_row_splits": [0, 2, 3],
         "ret_values": [0, 1, 2, 3, 4, 7, 8, 9], "ret_row_splits": [0, 5, 8]},
+    # farmhash::Fingerprint64 values the reference's own tests state (BloomFilterDifference hashes std::to_string(node) with it)
+    "fingerprint64": [
+        {"source": "tensorflow/python/kernel_tests/string_to_hash_bucket_op_test.py:46-49", "kind": "stated in reference test comments (the mod-10 buckets are asserted)",
+         "inputs": ["a", "b", "c", "d"], "values": [12917804110809363939, 11795596070477164822, 11430444447143000872, 4470636696479570465],
+         "mod10": [9, 2, 2, 5]},
+        {"source": "tensorflow/core/platform/fingerprint_test.cc:27-28", "kind": "asserted by reference test",
+         "inputs": ["Hello", "World"], "values": [15404698994557526151, 18308117990299812472]},
+    ],
+    # UO/bitmap_op/bloom_filter_difference.py:8-31: three chained calls on ONE flags variable (bucket=0, bucket_size=10);
+    # the script only prints, so the expected outputs are hand-derived from bitmap_ops.cc:334-359 (none of these 17 values
+    # collides in the 320-bit filter, so the results equal the exact-bitmap ones) and the final flags from the hash chain
+    "bloom_filter_difference_chain": {
+        "source": "UO/bitmap_op/bloom_filter_difference.py:8-31",
+        "kind": "hand-derived from bitmap_ops.cc:334-359 for the test's inputs",
+        "dtype": "int32", "bucket": 0, "bucket_size": 10, "flags0": [0] * 10,
+        "primes": [9277, 15031, 21433, 26557],           # find_prime_lower_than(29|47|67|83 * 10 * 32), :404-421
+        "calls": [
+            {"values": [1, 1, 2, 2, 3, 4, 5, 11, 12, 13], "row_splits": [0, 7, 10],
+             "c_values": [1, 2, 3, 4, 5, 11, 12, 13], "c_row_splits": [0, 5, 8]},
+            {"values": [4, 5, 6, 7, 7, 8, 10, 1000, 13, 14], "row_splits": [0, 7, 10],
+             "c_values": [6, 7, 8, 10, 1000, 14], "c_row_splits": [0, 4, 6]},
+            {"values": [4, 5, 6, 7, 7, 8, 10, 1000, 13, 14], "row_splits": [0, 7, 10],
+             "c_values": [], "c_row_splits": [0, 0, 0]},
+        ],
+        "flags_final": [536872960, 557842448, 541098520, 8194, -1598683056, -918413312, 176161152, -1560247680, 1090717705, 285212705],
+    },
     # UO/huge_const_op/huge_const_test.py:6-27 -- arrays saved then read back through HugeConst
     "huge_const": [
         {"source": "UO/huge_const_op/huge_const_test.py:6,22,25", "dtype": "int32", "array": [[1, 2], [3, 4], [5, 6]]},

@@ -285,3 +285,38 @@ def test_ragged_batch_helpers(nb):
     kept, new = ops.bitmap_difference(np.array([4, 9, 9, 40, 5, 127], np.int32), flags)
     assert kept.tolist() == [9, 40, 127] and flags.tolist() == [32254, 0, 0, 0]              # value semantics: input untouched
     assert new.view(np.uint32).tolist() == [32254 | (1 << 9), 1 << 8, 0, 1 << 31]
+
+
+def test_bloom_filter_difference(nb, oracle):
+    """BloomFilterDifference (bitmap_ops.cc:264-432): the reference script's chain (tests/golden), then random ragged
+    batches with heavy collisions / duplicates / negative and > 16-digit int64 ids / bucket > 0, against the oracle:
+    values, row_splits and the mutated flags must be identical."""
+    import json, os
+    rec = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "kat_ops.json")))["bloom_filter_difference_chain"]
+    flags = np.array(rec["flags0"], np.int32)
+    for call in rec["calls"]:
+        c, crs, _ = nb.bloom_filter_difference(np.array(call["values"], np.int32), np.array(call["row_splits"], np.int64), flags,
+                                               bucket=rec["bucket"], bucket_size=rec["bucket_size"])
+        assert c.tolist() == call["c_values"] and crs.tolist() == call["c_row_splits"]
+    assert flags.tolist() == rec["flags_final"]
+    rng = np.random.default_rng(5)
+    for dt, lo, hi, bucket, bsz in ((np.int32, 0, 3000, 0, 8), (np.int64, -50, 1 << 62, 1000003, 4), (np.int64, 0, 10 ** 9, 0, 64)):
+        g_flags, o_flags = np.zeros(bsz + 3, np.int32), np.zeros(bsz + 3, np.int32)
+        for _ in range(4):
+            n = int(rng.integers(1, 700))
+            vals = rng.integers(lo, hi, n).astype(dt)
+            vals[n // 2:] = vals[:n - n // 2]                       # duplicates inside the call
+            cuts = np.sort(rng.integers(0, n + 1, 5))
+            rs = np.concatenate([[0], cuts, [n]]).astype(np.int64)
+            c, crs, _ = nb.bloom_filter_difference(vals, rs, g_flags, bucket=bucket, bucket_size=bsz)
+            oc, ors, _ = oracle.bloom_filter_difference(vals, rs, o_flags, bucket, bsz)
+            np.testing.assert_array_equal(c, oc)
+            np.testing.assert_array_equal(crs, ors)
+            np.testing.assert_array_equal(g_flags, o_flags)
+    c, crs, _ = nb.bloom_filter_difference(np.zeros(0, np.int32), np.array([0], np.int64), np.zeros(2, np.int32), bucket_size=2)
+    assert c.size == 0 and crs.tolist() == [0]                      # void input (:312-322)
+    with pytest.raises(nb.NannError) as e:
+        nb.bloom_filter_difference(np.array([1, 2], np.int32), np.array([0, 3], np.int64), np.zeros(2, np.int32), bucket_size=2)
+    assert e.value.code == 3 and "code: 3" in str(e.value)
+    with pytest.raises(nb.NannError):
+        nb.bloom_filter_difference(np.array([1], np.int32), np.array([0, 1], np.int64), np.zeros(1, np.int32), bucket_size=2)

@@ -266,3 +266,74 @@ def test_batch_topk_on_rt_golden(oracle):
     assert v.size == 0 and i.size == 0 and rs.tolist() == [0]
     with pytest.raises(oracle.OracleError):
         oracle.batch_top_k_on_rt(c["values"], c["row_splits"], [1, 2])          # k vector length != groups
+
+
+def test_fingerprint64_golden(oracle):
+    """farmhash::Fingerprint64 restatement against the values the reference's own tests state"""
+    for rec in KAT["fingerprint64"]:
+        for s_, want in zip(rec["inputs"], rec["values"]):
+            assert oracle.fingerprint64(s_.encode()) == want, (rec["source"], s_)
+        if "mod10" in rec:
+            assert [oracle.fingerprint64(s_.encode()) % 10 for s_ in rec["inputs"]] == rec["mod10"]
+    assert oracle.fingerprint64(b"") == 0x9ae16a3b2f90404f
+
+
+def _py_bloom(values, row_splits, flags, bucket, bucket_size, fp):
+    """independent restatement of bitmap_ops.cc:334-359 in Python integers"""
+    import math
+    primes = []
+    for mp in (29, 47, 67, 83):
+        t = mp * bucket_size * 32
+        while not all(t % i for i in range(2, int(math.sqrt(t) + 1e-6) + 1)):
+            t -= 1
+        primes.append(t)
+    out, rs = [], [0]
+    for g in range(len(row_splits) - 1):
+        for j in range(row_splits[g], row_splits[g + 1]):
+            raw = fp(str(int(values[j])).encode())
+            if bucket > 0:
+                raw %= bucket
+            miss = 0
+            for l, mult in enumerate((1, 3, 5, 7)):
+                b = (((raw * mult) & ((1 << 64) - 1)) % primes[l]) % (bucket_size * 32)
+                w, bit = b >> 5, b & 31
+                if not (int(flags[w]) & 0xFFFFFFFF) >> bit & 1:
+                    miss += 1
+                    flags[w] = np.int32(np.uint32((int(flags[w]) & 0xFFFFFFFF) | (1 << bit)).view(np.int32)) if False else np.array([(int(flags[w]) & 0xFFFFFFFF) | (1 << bit)], np.uint32).view(np.int32)[0]
+            if miss:
+                out.append(int(values[j]))
+        rs.append(len(out))
+    return out, rs, primes
+
+
+def test_bloom_filter_difference_chain_golden(oracle):
+    rec = KAT["bloom_filter_difference_chain"]
+    flags = np.array(rec["flags0"], np.int32)
+    pflags = flags.copy()
+    for call in rec["calls"]:
+        c, crs, _ = oracle.bloom_filter_difference(np.array(call["values"], np.int32), call["row_splits"], flags,
+                                                   rec["bucket"], rec["bucket_size"])
+        assert c.tolist() == call["c_values"] and crs.tolist() == call["c_row_splits"]
+        pc, prs, primes = _py_bloom(call["values"], call["row_splits"], pflags, rec["bucket"], rec["bucket_size"], oracle.fingerprint64)
+        assert pc == call["c_values"] and prs == call["c_row_splits"] and primes == rec["primes"]
+    assert flags.tolist() == rec["flags_final"] and pflags.tolist() == rec["flags_final"]
+
+
+def test_bloom_filter_difference_random_vs_python(oracle):
+    """collisions, duplicates, int64 ids beyond 16 digits (the 17..32-byte hash branch), bucket > 0, void and bad input"""
+    rng = np.random.default_rng(3)
+    for dt, hi in ((np.int32, 2000), (np.int64, 1 << 62)):
+        flags = np.zeros(4, np.int32)                              # 128 bits: heavy collisions
+        pflags = flags.copy()
+        for _ in range(4):
+            vals = rng.integers(-5 if dt == np.int64 else 0, hi, 60).astype(dt)
+            vals[10:20] = vals[:10]
+            rs = [0, 25, 25, 60]
+            c, crs, _ = oracle.bloom_filter_difference(vals, rs, flags, 1000003, 4)
+            pc, prs, _ = _py_bloom(vals.tolist(), rs, pflags, 1000003, 4, oracle.fingerprint64)
+            assert c.tolist() == pc and crs.tolist() == prs
+            np.testing.assert_array_equal(flags, pflags)
+    c, crs, _ = oracle.bloom_filter_difference(np.zeros(0, np.int32), [0], np.zeros(2, np.int32), 0, 2)
+    assert c.size == 0 and crs.tolist() == [0]
+    with pytest.raises(oracle.OracleError):
+        oracle.bloom_filter_difference(np.array([1, 2], np.int32), [0, 3], np.zeros(2, np.int32), 0, 2)
