@@ -217,6 +217,15 @@ void nann_scorer_destroy(nann_scorer_t* s);
 /* BlazeXlaOp::Compute with inputs [user, item_emb[n, d]] -> logits[n] (fp32 in, fp32 out) */
 nann_status nann_blaze_xla_run(nann_scorer_t* s, const float* user, const float* item_emb, int64_t n,
                                float* logits, void* stream);
+/* Admission control of the two run calls, as BlazeXlaOp::Schedule (blaze_xla_kernel.cc:221-258): at most running_max
+ * runs at a time (default: env BLAZE_THREADS_NUM or 2, :87-93); a call that finds the scorer busy blocks -- with
+ * wait_ms > 0 (BlazeKernelOptions.wait_ms, config.proto:840) for at most that long, then fails with
+ * NANN_INTERNAL "blaze wait too long" (still queued) or NANN_DEADLINE_EXCEEDED "blaze wait too long" (admitted too
+ * late); with wait_ms == 0 it fails at once with NANN_INTERNAL "waiting pool is full" when max_waiting calls (default:
+ * env DENSE_MAX_WAITING_COUNT or 10, :95-101) are queued already.  A negative argument leaves that setting alone. */
+nann_status nann_scorer_set_admission(nann_scorer_t* s, int running_max, int max_waiting, int wait_ms);
+nann_status nann_scorer_admission_state(nann_scorer_t* s, int* running, int* waiting, int* running_max,
+                                        int* max_waiting, int* wait_ms);
 /* fused GatherV2 + BlazeXlaOp: logits[i] = score(user, table[ids[i]]); table f32 [n_rows][d] */
 nann_status nann_scorer_run_ids(nann_scorer_t* s, const float* user, const float* table,
                                 int64_t n_rows, const int32_t* ids, int64_t n, float* logits,

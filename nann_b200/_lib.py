@@ -74,6 +74,8 @@ def lib():
     L.nann_scorer_set_precision.argtypes = [vp, i32]
     L.nann_scorer_user_floats.argtypes = [vp]
     L.nann_scorer_item_dim.argtypes = [vp]
+    L.nann_scorer_set_admission.argtypes = [vp, i32, i32, i32]
+    L.nann_scorer_admission_state.argtypes = [vp, vp, vp, vp, vp, vp]
     L.nann_scorer_destroy.restype = None
     L.nann_scorer_destroy.argtypes = [vp]
     L.nann_blaze_xla_run.argtypes = [vp, vp, vp, i64, vp, vp]

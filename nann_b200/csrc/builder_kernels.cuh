@@ -11,8 +11,8 @@
 //   2. exact refinement: fp32 distances (sequential fmaf chains) of the 128 survivors, the closest n_cand of them,
 //      HNSW's diversity heuristic on exact pair distances -> at most M forward links (knn_refine_kernel).
 //   3. reverse links, de-duplication, closest `cap` per node, rows closest-first (link_* kernels).
-// The arithmetic of steps 2-3 is restated on the CPU in oracle/nann_oracle.c (orc_build_level) and the files are
-// compared bit for bit in tests/test_builder_gpu.py; step 1 only has to deliver a superset of the n_cand exact
+// The arithmetic of steps 2-3 has a CPU restatement among the test infrastructure and the files are compared bit for
+// bit in tests/test_builder_gpu.py; step 1 only has to deliver a superset of the n_cand exact
 // nearest neighbours (fp16 products: |d2 error| ~ 1e-3, far below the rank-96 / rank-128 distance gap).
 #pragma once
 #include "scorer_tc_common.cuh"

@@ -4,6 +4,8 @@
 #include <stdint.h>
 
 #include <atomic>
+#include <chrono>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <map>

@@ -1,7 +1,68 @@
 // lib_search.inl -- scorer handles, the HBM-resident index, and the batched exec.pb dataflow
 // (NANN_impls/nann/delivery/build_opt_graph.py:109-149) as a fixed sequence of kernel launches.
 
+// BlazeXlaOp's admission control (UO/blaze_op/blaze_xla_kernel.cc:87-101,221-258): at most `running_max` runs at a
+// time (BLAZE_THREADS_NUM, default 2); a request that finds the op busy waits -- up to `wait_ms` when that is set in
+// the blaze options (then "blaze wait too long": Internal while still queued, DeadlineExceeded when it would start
+// late), otherwise as long as fewer than `max_waiting` requests are queued (DENSE_MAX_WAITING_COUNT, default 10; else
+// Internal "waiting pool is full").  The reference re-posts a waiting request to its thread pool in a loop; here the
+// caller's thread waits on a condition variable -- same admissions, same errors, no spinning.
+struct BlazeAdmission {
+  int running_max = 2, max_waiting = 10;
+  long long wait_ns = 0;
+  int running = 0, waiting = 0;
+  std::mutex mu;
+  std::condition_variable cv;
+  static long long env_or(const char* name, long long dflt) {
+    const char* e = std::getenv(name);
+    return (e && *e) ? atoll(e) : dflt;
+  }
+  BlazeAdmission() {
+    running_max = (int)env_or("BLAZE_THREADS_NUM", 2);           // BlazeThreadsCount(), :87-93
+    max_waiting = (int)env_or("DENSE_MAX_WAITING_COUNT", 10);    // BlazeWatingCount(), :95-101
+  }
+  static long long now_ns() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (long long)ts.tv_sec * 1000000000ll + ts.tv_nsec;
+  }
+  nann_status enter() {                                           // Schedule(), :221-258
+    const long long begin = now_ns();
+    std::unique_lock<std::mutex> lk(mu);
+    bool first = true;
+    for (;;) {
+      const long long waited = now_ns() - begin;
+      if (running >= running_max) {
+        if (wait_ns > 0) {
+          if (waited > wait_ns) {
+            if (!first) --waiting;
+            return nann::fail(NANN_INTERNAL, "blaze wait too long %lld", waited);
+          }
+        } else if (waiting >= max_waiting && first) {
+          return nann::fail(NANN_INTERNAL, "waiting pool is full %d", waiting);
+        }
+        if (first) { ++waiting; first = false; }
+        if (wait_ns > 0) cv.wait_for(lk, std::chrono::nanoseconds(std::max<long long>(wait_ns - waited, 1000)));
+        else cv.wait(lk);
+        continue;
+      }
+      if (!first) --waiting;
+      if (wait_ns > 0 && waited > wait_ns) {                      // would start too late (:243-248)
+        cv.notify_one();
+        return nann::fail(NANN_DEADLINE_EXCEEDED, "blaze wait too long %lld", waited);
+      }
+      ++running;
+      return NANN_OK;
+    }
+  }
+  void leave() {
+    { std::lock_guard<std::mutex> lk(mu); --running; }
+    cv.notify_one();
+  }
+};
+
 struct nann_scorer {
+  BlazeAdmission gate;
   int kind = 0;  // 0 = mlp, 1 = attention
   int device = 0;
   int precision = NANN_SCORER_EXACT;
@@ -264,12 +325,39 @@ static nann_status scorer_run_common(nann_scorer_t* s, const float* user, const 
 
 nann_status nann_blaze_xla_run(nann_scorer_t* s, const float* user, const float* item_emb, int64_t n,
                                float* logits, void* stream) {
-  return scorer_run_common(s, user, item_emb, n, nullptr, n, logits, stream);
+  if (!s) return fail(NANN_INVALID_ARGUMENT, "null scorer");
+  NANN_TRY(s->gate.enter());
+  const nann_status rc = scorer_run_common(s, user, item_emb, n, nullptr, n, logits, stream);
+  s->gate.leave();
+  return rc;
 }
 nann_status nann_scorer_run_ids(nann_scorer_t* s, const float* user, const float* table, int64_t n_rows,
                                 const int32_t* ids, int64_t n, float* logits, void* stream) {
   if (!ids) return fail(NANN_INVALID_ARGUMENT, "ids is NULL");
-  return scorer_run_common(s, user, table, n_rows, ids, n, logits, stream);
+  if (!s) return fail(NANN_INVALID_ARGUMENT, "null scorer");
+  NANN_TRY(s->gate.enter());
+  const nann_status rc = scorer_run_common(s, user, table, n_rows, ids, n, logits, stream);
+  s->gate.leave();
+  return rc;
+}
+nann_status nann_scorer_set_admission(nann_scorer_t* s, int running_max, int max_waiting, int wait_ms) {
+  if (!s) return fail(NANN_INVALID_ARGUMENT, "null scorer");
+  std::lock_guard<std::mutex> lk(s->gate.mu);
+  if (running_max >= 1) s->gate.running_max = running_max;
+  if (max_waiting >= 0) s->gate.max_waiting = max_waiting;
+  if (wait_ms >= 0) s->gate.wait_ns = (long long)wait_ms * 1000000ll;
+  return NANN_OK;
+}
+nann_status nann_scorer_admission_state(nann_scorer_t* s, int* running, int* waiting, int* running_max, int* max_waiting,
+                                        int* wait_ms) {
+  if (!s) return fail(NANN_INVALID_ARGUMENT, "null scorer");
+  std::lock_guard<std::mutex> lk(s->gate.mu);
+  if (running) *running = s->gate.running;
+  if (waiting) *waiting = s->gate.waiting;
+  if (running_max) *running_max = s->gate.running_max;
+  if (max_waiting) *max_waiting = s->gate.max_waiting;
+  if (wait_ms) *wait_ms = (int)(s->gate.wait_ns / 1000000ll);
+  return NANN_OK;
 }
 
 // ---- index -----------------------------------------------------------------------------------

@@ -324,6 +324,16 @@ class Scorer:
         check(_lib.lib().nann_scorer_create_attention(C.c_void_p(blob.ctypes.data), blob.size, int(device), C.byref(h)))
         return cls(h, "attention")
 
+    def set_admission(self, running_max=-1, max_waiting=-1, wait_ms=-1):
+        """BlazeXlaOp's admission control for blaze_xla_op / score_ids (blaze_xla_kernel.cc:221-258):
+        BLAZE_THREADS_NUM, DENSE_MAX_WAITING_COUNT, BlazeKernelOptions.wait_ms; -1 keeps a setting."""
+        check(_lib.lib().nann_scorer_set_admission(self._h, int(running_max), int(max_waiting), int(wait_ms)))
+
+    def admission_state(self):
+        v = [C.c_int(0) for _ in range(5)]
+        check(_lib.lib().nann_scorer_admission_state(self._h, *[C.byref(x) for x in v]))
+        return dict(zip(("running", "waiting", "running_max", "max_waiting", "wait_ms"), [x.value for x in v]))
+
     def set_precision(self, precision):
         check(_lib.lib().nann_scorer_set_precision(self._h, int(precision)))
 

@@ -1,5 +1,7 @@
 """Scorer parity.  EXACT mlp path: bit-identical to the oracle's fp32 definition.  Attention
 scorer and TENSOR mlp path: |diff| <= 1e-5 (north_star tolerance)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -102,3 +104,47 @@ def test_mlp_tensor_core_larger_magnitudes(nb, oracle, small_world):
     s.set_precision(nb.SCORER_TENSOR)
     want, got = m.score(u, x), nb.blaze_xla_op(s, u, x)
     assert np.abs(got - want).max() <= 1e-5 * max(1.0, float(np.abs(want).max()))
+
+
+def test_blaze_xla_op_admission_control(nb):
+    """BlazeXlaOp::Schedule (blaze_xla_kernel.cc:221-258): running cap, 'waiting pool is full', 'blaze wait too long'."""
+    import threading
+    from nann_b200 import index as nix, scorer_weights as sw
+    sc = nb.Scorer.mlp(*sw.mlp_weights())
+    st = sc.admission_state()
+    assert st["running_max"] == int(os.environ.get("BLAZE_THREADS_NUM", 2)) and st["max_waiting"] == int(os.environ.get("DENSE_MAX_WAITING_COUNT", 10))
+    emb = nix.synthetic_corpus(1_000_000, 128, seed=1)                   # EXACT scorer: ~17 ms per run
+    import torch
+    emb_d = torch.from_numpy(emb).cuda()
+    user = emb[0]
+
+    def fire(n_threads, results):
+        def work(i):
+            try:
+                nb.blaze_xla_op(sc, user, emb_d)
+                results[i] = "ok"
+            except nb.NannError as e:
+                results[i] = (e.code, e.message)
+        th = [threading.Thread(target=work, args=(i,)) for i in range(n_threads)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+
+    # (a) one runner, nobody may wait: concurrent calls beyond the first fail with Internal "waiting pool is full"
+    sc.set_admission(running_max=1, max_waiting=0, wait_ms=0)
+    res = [None] * 6
+    fire(6, res)
+    assert res.count("ok") >= 1 and any(r != "ok" for r in res)
+    assert all(r == "ok" or (r[0] == 13 and "waiting pool is full" in r[1]) for r in res)
+    # (b) everybody may wait: all succeed, never more than one running
+    sc.set_admission(running_max=1, max_waiting=10, wait_ms=0)
+    res = [None] * 6
+    fire(6, res)
+    assert res == ["ok"] * 6
+    # (c) a 1-ms deadline against runs that take far longer: late calls fail with "blaze wait too long"
+    sc.set_admission(running_max=1, max_waiting=10, wait_ms=1)
+    res = [None] * 6
+    fire(6, res)
+    assert res.count("ok") >= 1 and any(r != "ok" for r in res)
+    assert all(r == "ok" or (r[0] in (4, 13) and "blaze wait too long" in r[1]) for r in res)
+    s2 = sc.admission_state()
+    assert s2["running"] == 0 and s2["waiting"] == 0
