@@ -403,31 +403,82 @@ def run_b200(args, T, rank, world, local_rank):
 
     recall_target = None
     if world > 1 and truth is not None and args.shard_scale <= 0:
+        from nann_b200 import distributed as nd
+        # a second, independent query set drives the calibration; the recall that is REPORTED (and checked against the
+        # one-GPU operating point) is measured on eval_q afterwards
+        cal_q = nix().synthetic_queries(query_pool(args.n_items), n_eval, seed=6)
+        emb_dev = torch.from_numpy(sh["emb"]).to(dev)
+        truth_cal = Truth(nb, sc, emb_dev, torch.from_numpy(sh["item_ids"]).to(dev), cal_q, k, world, dev)
+        del emb_dev
+        torch.cuda.empty_cache()
         # the one-GPU operating point: rank 0 searches the UNSHARDED index with the full beams
+        cal_target = None
         if args.n_items <= BIG:
-            rt = torch.zeros(1, dtype=torch.float64, device=dev)
+            rt = torch.zeros(3, dtype=torch.float64, device=dev)
             if rank == 0:
                 t0 = time.time()
                 sh1 = get_shard(args.n_items, 1, 0, dev)
                 ix1 = nb.Index.from_arrays(sh1["emb"], sh1["item_ids"], sh1["ep"], sh1["values"], sh1["row_splits"], device=local_rank)
                 se1 = nb.Searcher(ix1, sc, n_eval, T)
-                rt[0] = truth.recall(se1.search(eval_q[:n_eval], T)["ids"])
+                r1 = se1.search(eval_q[:n_eval], T)
+                rt[0] = truth.recall(r1["ids"])
+                rt[1] = truth_cal.recall(se1.search(cal_q, T)["ids"])
+                rt[2] = float(r1["n_scored"].sum()) / n_eval
                 del se1, ix1, sh1
-                log(f"[bench] one-GPU operating point: recall@{k} = {rt.item():.4f} ({time.time() - t0:.1f}s)")
+                log(f"[bench] one-GPU operating point: recall@{k} = {rt[0].item():.4f} ({rt[1].item():.4f} on the calibration queries), "
+                    f"{rt[2].item():.0f} rows scored per query ({time.time() - t0:.1f}s)")
             dist.broadcast(rt, 0)
-            recall_target = rt.item()
-        # smallest per-shard beam scale that holds it
+            recall_target, cal_target = rt[0].item(), rt[1].item()
+            extra["one_gpu_rows_scored_per_query"] = rt[2].item()
+        cal_dev = torch.from_numpy(cal_q).to(dev)
         trials = []
-        for s_ in SCALES:
-            Ts_ = shard_topn(T, world, s_)
+
+        def evaluate(scales):
+            """-> (recall on the calibration queries, rows scored per query summed over the shards)"""
+            Ts_ = nd.shard_beams(T, world, scales)
             se_ = nb.Searcher(ix, sc, n_eval, Ts_)
-            rec = truth.recall(sharded_host(se_, eval_q[:n_eval], Ts_)[0])
+            o_i = torch.empty((n_eval, Ts_[5]), dtype=torch.int64, device=dev)
+            o_s = torch.empty((n_eval, Ts_[5]), dtype=torch.float32, device=dev)
+            _, m_id, _, stats = nd.sharded_search(se_, cal_dev, Ts_, k, o_i, o_s, nb.merge_topk)
+            rows_ = torch.tensor([float(stats["n_scored"].sum())], dtype=torch.float64, device=dev)
+            dist.all_reduce(rows_)
+            rec = truth_cal.recall(np.asarray(m_id))
+            trials.append({"scales": [round(float(x), 4) for x in scales], "shard_level_topn": Ts_, "recall": rec,
+                           "rows_scored_per_query": rows_.item() / n_eval})
+            return rec, rows_.item() / n_eval
+
+        # (1) smallest uniform scale that holds the target
+        scales = None
+        for s_ in SCALES:
+            rec, _ = evaluate([s_] * 5)
+            scales = [s_] * 5
+            if cal_target is None or rec >= cal_target - RECALL_TOL:
+                break
+        # (2) lower the beams one by one while the target still holds (each accepted step scores fewer rows)
+        if cal_target is not None:
+            improved = True
+            while improved and len(trials) < 60:
+                improved = False
+                for l in range(5):
+                    cand = list(scales)
+                    cand[l] = cand[l] * 0.85
+                    if nd.shard_beams(T, world, cand) == nd.shard_beams(T, world, scales):
+                        continue
+                    rec, _ = evaluate(cand)
+                    if rec >= cal_target - RECALL_TOL:
+                        scales, improved = cand, True
+        # (3) check on the report queries; widen everything a notch if the independent set disagrees
+        for _ in range(6):
+            Ts = nd.shard_beams(T, world, scales)
+            se_ = nb.Searcher(ix, sc, n_eval, Ts)
+            rec = truth.recall(sharded_host(se_, eval_q[:n_eval], Ts)[0])
             del se_
-            trials.append({"scale": s_, "shard_level_topn": Ts_, "recall": rec})
-            Ts, scale = Ts_, s_
             if recall_target is None or rec >= recall_target - RECALL_TOL:
                 break
+            scales = [x * 1.06 for x in scales]
+        scale = [round(float(x), 4) for x in scales]
         extra["calibration"] = trials
+        del cal_dev
     elif world > 1:
         scale = args.shard_scale if args.shard_scale > 0 else 1.0
         Ts = shard_topn(T, world, scale)

@@ -35,6 +35,15 @@ def shard_level_topn(T, world, scale=1.0):
     return t + [k]
 
 
+def shard_beams(T, world, scales):
+    """shard_level_topn with one scale per beam (T[0..4]); the calibration pass of bench.py lowers them one by one"""
+    if world == 1:
+        return [int(t) for t in T]
+    t = [max(int(-(-float(x) * float(s) // world)), 8) for x, s in zip(T[:5], scales)]
+    k = min(max(-(-int(T[5]) // world) * 2, 16), sum(t[1:5]))
+    return t + [k]
+
+
 def combine_status(status_by_shard):
     """[G, B] per-shard status -> [B]: the first failing shard decides (a query that fails anywhere fails)."""
     st = np.asarray(status_by_shard, np.int32)
