@@ -74,7 +74,9 @@ def tensor(buf):
         elif f == 6:
             vals += list(np.frombuffer(bytes(v), "<f8")) if wt == 2 else [struct.unpack("<d", struct.pack("<Q", v))[0]]
         elif f in (7, 10, 13):                                # int_val / int64_val / half_val (bit patterns)
-            vals += packed_varints(v) if wt == 2 else [v]
+            raw = packed_varints(v) if wt == 2 else [v]
+            # negative int32 / int64 values travel as 64-bit two's-complement varints
+            vals += [x - (1 << 64) if (f != 13 and x >> 63) else x for x in raw]
     if dtype not in DT:
         return None
     np_t = DT[dtype]

@@ -27,7 +27,8 @@ constexpr int KB_STRIP = 16;        // column tiles per work item
 constexpr int KB_THREADS = 320;     // warp 0 producer, warp 1 MMA, warps 2..9 filter epilogue
 constexpr int KB_A_BYTES = 32768;   // 128 rows x 128 k fp16
 constexpr int KB_B_BYTES = 65536;   // 256 rows x 128 k fp16
-constexpr int KB_SMEM_BYTES = 2 * KB_A_BYTES + 2 * KB_B_BYTES + 1024;
+constexpr int KB_HJ_SLOTS = 8;      // column-norm ring: the producer is at most 4 tiles ahead of the slowest epilogue thread
+constexpr int KB_SMEM_BYTES = 2 * KB_A_BYTES + 2 * KB_B_BYTES + KB_HJ_SLOTS * KB_TN * 4 + 1024;
 constexpr int KB_MAX_CAND = 96;     // n_cand limit of the refine kernel (cap + M at level 0 with M = 32)
 
 // ---- exact row norms: sq[r] = sum_k x[k]^2, sequential fmaf chain in k (the oracle's definition)
@@ -92,7 +93,8 @@ knn_filter_kernel(KnnArgs p) {
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* sA = smem;                         // 2 x 32 KB
   uint8_t* sB = smem + 2 * KB_A_BYTES;        // 2 x 64 KB
-  uint64_t* bars = (uint64_t*)(sB + 2 * KB_B_BYTES);
+  float* hj_s = (float*)(sB + 2 * KB_B_BYTES);                  // [KB_HJ_SLOTS][256] sq_j / 2 of the tile's columns
+  uint64_t* bars = (uint64_t*)(hj_s + KB_HJ_SLOTS * KB_TN);
   uint32_t* tmem_slot = (uint32_t*)(bars + 16);
   enum { A_FULL = 0, A_EMPTY = 2, B_FULL = 4, B_EMPTY = 6, D_FULL = 8, D_EMPTY = 10 };
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -144,9 +146,12 @@ knn_filter_kernel(KnnArgs p) {
         mbar_wait(BAR(B_EMPTY + st), ((ib >> 1) & 1) ^ 1);
         if (elect_one()) {
           const int64_t cb = (p.col0 >> 8) + ct0 + t;          // 256-row block of the image
-          mbar_expect_tx(BAR(B_FULL + st), KB_B_BYTES);
+          // the column norms ride along (a global load per compare missed the few-KB L1 on every tile: 8.5k cycles per
+          // tile instead of ~1.2k).  Slot ib % 8 is free: B ring (2) + accumulator ring (2) keep this warp < 8 tiles ahead.
+          mbar_expect_tx(BAR(B_FULL + st), KB_B_BYTES + KB_TN * 4);
           bulk_g2s(smem_u32(sB) + st * KB_B_BYTES, p.img + cb * KB_B_BYTES, 32768, BAR(B_FULL + st));
           bulk_g2s(smem_u32(sB) + st * KB_B_BYTES + 32768, p.img + cb * KB_B_BYTES + 32768, 32768, BAR(B_FULL + st));
+          bulk_g2s(smem_u32(hj_s) + (ib % KB_HJ_SLOTS) * KB_TN * 4, p.hj + cb * KB_TN, KB_TN * 4, BAR(B_FULL + st));
         }
       }
     }
@@ -198,6 +203,7 @@ knn_filter_kernel(KnnArgs p) {
         mbar_wait(BAR(D_FULL + st), (ib >> 1) & 1);
         tc_fence_after();
         const int64_t c_tile = p.col0 + (int64_t)(ct0 + t) * KB_TN + col_half * 128;
+        const float* hj_t = hj_s + (ib % KB_HJ_SLOTS) * KB_TN + col_half * 128;
         const uint32_t tb = tmem + t_lane + st * 256 + (uint32_t)(col_half * 128);
 #pragma unroll 1
         for (int ch = 0; ch < 4; ++ch) {
@@ -206,7 +212,7 @@ knn_filter_kernel(KnnArgs p) {
           const int64_t c0 = c_tile + ch * 32;
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
-            const float4 h = __ldg(reinterpret_cast<const float4*>(p.hj + c0 + g * 4));
+            const float4 h = *reinterpret_cast<const float4*>(hj_t + ch * 32 + g * 4);
             // pass <=> tau > sq_i + sq_j - 2 dot  <=>  dot - sq_j/2 > (sq_i - tau)/2
             const bool p0 = (__uint_as_float(v[g * 4 + 0]) - h.x) > hi, p1 = (__uint_as_float(v[g * 4 + 1]) - h.y) > hi;
             const bool p2 = (__uint_as_float(v[g * 4 + 2]) - h.z) > hi, p3 = (__uint_as_float(v[g * 4 + 3]) - h.w) > hi;
