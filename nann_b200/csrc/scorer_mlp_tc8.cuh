@@ -98,7 +98,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
     if (!done && (spin & 63) == 63) {
       const unsigned long long now = global_ns();
       if (t0 == 0) t0 = now;
-      else if (now - t0 > 2000000000ull) __trap();
+      else if (NANN_MBAR_WATCHDOG_NS && now - t0 > NANN_MBAR_WATCHDOG_NS) __trap();
     }
   }
 }
@@ -118,7 +118,7 @@ __device__ __forceinline__ void mbar_wait_lean(uint32_t bar, uint32_t parity) {
                  "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 1000000;\n\t"
                  "selp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    if (spin > 4000) __trap();
+    if (NANN_MBAR_WATCHDOG_NS && spin > (uint32_t)(NANN_MBAR_WATCHDOG_NS / 1000000ull)) __trap();   // each try_wait suspends up to 1 ms
   }
 }
 

@@ -26,8 +26,13 @@ __device__ __forceinline__ unsigned long long global_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-// Never hang the GPU: a wait that lasts longer than 2 s of wall clock (a lost arrival, i.e. a
-// pipeline bug) turns into a trap -> a CUDA error on the host instead of a dead device.
+// Never hang the GPU: a wait that lasts longer than NANN_MBAR_WATCHDOG_NS of wall clock (a lost arrival, i.e. a
+// pipeline bug) turns into a trap -> a CUDA error on the host instead of a dead device.  10 s by default: long enough
+// for a debugger single-step, an MPS time slice or compute-sanitizer's instrumentation (racecheck slows these kernels
+// ~100x; build with -DNANN_MBAR_WATCHDOG_NS=0 to compile the watchdog out).
+#ifndef NANN_MBAR_WATCHDOG_NS
+#define NANN_MBAR_WATCHDOG_NS 10000000000ull
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
   unsigned long long t0 = 0;
@@ -48,7 +53,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (!done && (spin & 63) == 63) {
       const unsigned long long now = global_ns();
       if (t0 == 0) t0 = now;
-      else if (now - t0 > 2000000000ull) __trap();
+      else if (NANN_MBAR_WATCHDOG_NS && now - t0 > NANN_MBAR_WATCHDOG_NS) __trap();
     }
   }
 }
@@ -85,7 +90,7 @@ __device__ __forceinline__ void mbar_wait_warp_relaxed(uint32_t bar, uint32_t pa
       if ((spin & 63) == 63) {
         const unsigned long long now = global_ns();
         if (t0 == 0) t0 = now;
-        else if (now - t0 > 2000000000ull) __trap();
+        else if (NANN_MBAR_WATCHDOG_NS && now - t0 > NANN_MBAR_WATCHDOG_NS) __trap();
       }
     }
   }

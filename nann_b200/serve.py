@@ -240,6 +240,28 @@ def searcher_backend(searcher):
     return run
 
 
+def load_scorer(nb, sw, kind, weights, synthetic):
+    """the scorer the endpoint ranks with: trained weights from a file, or -- only when asked for explicitly -- seeded
+    random ones.  Refuses to start without either: a server ranking by random weights looks healthy and is useless."""
+    import numpy as np
+    if weights is None:
+        if not synthetic:
+            raise SystemExit("--scorer-weights is required (an .npy blob, frozen_graph.pb or checkpoint prefix); "
+                             "pass --synthetic to serve seeded random weights")
+        return nb.Scorer.attention(sw.attention_blob(seed=3)) if kind == "attention" else nb.Scorer.mlp(*sw.mlp_weights(seed=3))
+    if kind == "mlp":
+        z = np.load(weights)
+        return nb.Scorer.mlp(z["W1"], z["b1"], z["W2"], z["b2"], z["w3"])
+    from nann_b200 import tf_import
+    if weights.endswith(".npy"):
+        blob = np.load(weights)
+    elif weights.endswith(".pb"):
+        blob = tf_import.attention_blob_from_frozen_graph(weights)
+    else:
+        blob = tf_import.attention_blob_from_checkpoint(weights)
+    return nb.Scorer.attention(np.ascontiguousarray(blob, np.float32))
+
+
 def main():
     import uvicorn
     import nann_b200 as nb
@@ -250,14 +272,22 @@ def main():
     ap.add_argument("--max-level-topn", default="100,200,400,400,400,200")
     ap.add_argument("--max-batch-size", type=int, default=256)
     ap.add_argument("--batch-timeout-us", type=int, default=200)
-    ap.add_argument("--precision", default="tensor", choices=["exact", "tensor"])
+    ap.add_argument("--scorer", default="attention", choices=["attention", "mlp"],
+                    help="attention = the reference's model (Model.forward, 64-d item embeddings); mlp = the 2x512 bench scorer (128-d)")
+    ap.add_argument("--scorer-weights", default=None,
+                    help="attention: an .npy blob (scorer_weights.py layout), a frozen_graph.pb (convert_meta.py output) or a "
+                         "checkpoint prefix; mlp: an .npz with W1,b1,W2,b2,w3")
+    ap.add_argument("--synthetic", action="store_true", help="serve seeded random weights (smoke tests only)")
+    ap.add_argument("--precision", default=None, choices=["exact", "tensor"], help="mlp only; default tensor")
     ap.add_argument("--host", default="0.0.0.0")
     ap.add_argument("--port", type=int, default=8501)
     ap.add_argument("--grpc-port", type=int, default=8500, help="0 = REST only")
     args = ap.parse_args()
     ix = nb.Index.load(args.embs_dir, args.index_dir)
-    sc = nb.Scorer.mlp(*sw.mlp_weights(seed=3))      # seeded mlp2x512 weights (the bench scorer); see tf_import.py for frozen graphs
-    if args.precision == "tensor":
+    sc = load_scorer(nb, sw, args.scorer, args.scorer_weights, args.synthetic)
+    if sc.item_dim != ix.dim:
+        raise SystemExit(f"--scorer {args.scorer} expects {sc.item_dim}-d item embeddings, the index has {ix.dim}-d rows")
+    if args.scorer == "mlp" and (args.precision or "tensor") == "tensor":
         sc.set_precision(nb.SCORER_TENSOR)
     se = nb.Searcher(ix, sc, args.max_batch_size, [int(t) for t in args.max_level_topn.split(",")])
     lock = threading.Lock()                         # one searcher, two front-ends: serialise the backend calls

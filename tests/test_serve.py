@@ -135,3 +135,18 @@ def test_grpc_prediction_service_predict():
     finally:
         server.stop(0)
         batcher.close()
+
+
+def test_serving_cli_refuses_to_rank_with_random_weights():
+    """the CLI must not silently serve a randomly initialised scorer"""
+    from nann_b200 import serve
+
+    class _NB:
+        class Scorer:
+            attention = staticmethod(lambda blob: ("attention", len(blob)))
+            mlp = staticmethod(lambda *w: ("mlp", len(w)))
+    from nann_b200 import scorer_weights as sw
+    with pytest.raises(SystemExit):
+        serve.load_scorer(_NB, sw, "attention", None, synthetic=False)
+    assert serve.load_scorer(_NB, sw, "attention", None, synthetic=True) == ("attention", sw.ATT_BLOB)
+    assert serve.load_scorer(_NB, sw, "mlp", None, synthetic=True) == ("mlp", 5)
