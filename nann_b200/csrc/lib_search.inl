@@ -507,6 +507,13 @@ struct nann_searcher {
   nann::TcWorkspace* tcws = nullptr;                        // tensor-core scorer scratch (lazy)
   bool trace = false;
   int32_t* tr_ids = nullptr; float* tr_sc = nullptr;       // [5][maxB][maxc] when tracing
+  // CUDA graphs of the launch sequence for small batches, keyed by (B, level_topn, scorer precision)
+  struct GraphKey {
+    int B, precision, T[6];
+    bool operator<(const GraphKey& o) const { return memcmp(this, &o, sizeof(GraphKey)) < 0; }
+  };
+  struct GraphVal { cudaGraphExec_t exec = nullptr; uint64_t kernels = 0; };   // kernels per replay (for the launch counter)
+  std::map<GraphKey, GraphVal> graphs;
   // host mirrors of the last call
   std::vector<int32_t> h_round_n, h_round_exp, h_status;
   int last_B = 0, last_k = 0;
@@ -529,6 +536,7 @@ void nann_searcher_destroy(nann_searcher_t* s) {
   cudaFree(s->res_ids); cudaFree(s->res_sc); cudaFree(s->out_nodes); cudaFree(s->out_sc);
   cudaFree(s->out_item); cudaFree(s->status); cudaFree(s->tr_ids); cudaFree(s->tr_sc);
   for (auto e : s->ev) cudaEventDestroy(e);
+  for (auto& kv : s->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   if (s->tcws) { nann::tc_ws_free(s->tcws); delete s->tcws; }
   delete s;
 }
@@ -603,25 +611,24 @@ namespace nann {
 // the searcher's out_sc / out_nodes / out_item ([B][max(k,1)]), per-query status and the per-round counters in
 // s->status / s->round_n / s->round_exp.  `push` (optional) makes the final top-k deliver its records to the shard
 // group's windows as well (lib_shard.inl).
-static nann_status search_enqueue(nann_searcher* s, const float* users, int B, const int32_t T[6], cudaStream_t st,
-                                  const ShardPush* push) {
+__global__ void copy_floats_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+// everything after the users are in s->users: a fixed launch sequence whose arguments depend only on
+// (searcher, B, level_topn, scorer precision) -- which is what makes it capturable as a CUDA graph
+static nann_status search_core(nann_searcher* s, int B, const int32_t T[6], cudaStream_t st, const ShardPush* push) {
   const nann_index* ix = s->ix;
-  const int uf = nann_scorer_user_floats(s->sc);
   const int64_t mb = s->max_batch;
   const int k = T[5];
-
-  // users -> device workspace (H2D when the caller passed host memory; inside the init kernel otherwise) and the
-  // per-call state, in ONE kernel (no memset nodes: see fill_words_kernel)
-  const bool users_dev = is_device_ptr(users);
-  if (!users_dev) NANN_CUDA(cudaMemcpyAsync(s->users, users, (size_t)B * uf * 4, cudaMemcpyHostToDevice, st));
-  {
+  {   // per-call state in ONE kernel (no memset nodes: see fill_words_kernel)
     SearchInitArgs ia{};
     ia.status = s->status; ia.B = B;
     ia.round_n = s->round_n; ia.round_exp = s->round_exp; ia.n_round = 5 * mb;
     ia.out_item_w = (uint32_t*)s->out_item; ia.out_sc_w = (uint32_t*)s->out_sc; ia.out_nodes_w = (uint32_t*)s->out_nodes;
     ia.n_out = (int64_t)B * k;
-    ia.users_src = users_dev ? users : nullptr; ia.users_dst = s->users; ia.n_users = (int64_t)B * uf;
-    const int64_t work = std::max<int64_t>(std::max<int64_t>(ia.n_round, ia.n_out), ia.n_users);
+    ia.users_src = nullptr; ia.users_dst = s->users; ia.n_users = 0;
+    const int64_t work = std::max<int64_t>(std::max<int64_t>(ia.n_round, ia.n_out), 1);
     NANN_LAUNCH(search_init_kernel, (unsigned)std::min<int64_t>(ceil_div(work, 256), 148 * 4), 256, 0, st, ia);
   }
   NANN_TRY(scorer_prepare_users(s->sc, s->users, B, s->ustate, st));
@@ -753,7 +760,62 @@ static nann_status search_enqueue(nann_searcher* s, const float* users, int B, c
     if (push) a.push = *push;
     NANN_TRY(topk_timed(a));
   }
-  s->last_B = B; s->last_k = k;
+  return NANN_OK;
+}
+
+// Small batches are launch-bound (batch 1: ~31 launches for ~0.2 ms of GPU work), so the core sequence of a
+// (B, level_topn, precision) key is captured into a CUDA graph the second time the key is seen (the first call runs
+// eagerly and sizes every lazily grown buffer) and replayed with ONE launch afterwards.  Not used while tracing or
+// profiling (those add per-call work) or for the sharded push (its arguments carry the sequence number).
+static nann_status search_enqueue(nann_searcher* s, const float* users, int B, const int32_t T[6], cudaStream_t st,
+                                  const ShardPush* push) {
+  const int uf = nann_scorer_user_floats(s->sc);
+  if (is_device_ptr(users))
+    NANN_LAUNCH(copy_floats_kernel, (unsigned)std::min<int64_t>(ceil_div((int64_t)B * uf, 256), 148 * 4), 256, 0, st, users, s->users, (int64_t)B * uf);
+  else
+    NANN_CUDA(cudaMemcpyAsync(s->users, users, (size_t)B * uf * 4, cudaMemcpyHostToDevice, st));
+  s->last_B = B; s->last_k = T[5];
+  static const int graph_max_b = [] { const char* e = std::getenv("NANN_GRAPH_MAX_BATCH"); return e ? atoi(e) : 32; }();
+  if (push || s->trace || s->profile || B > graph_max_b) return search_core(s, B, T, st, push);
+  nann_searcher::GraphKey key{};
+  key.B = B; key.precision = s->sc->precision;
+  for (int i = 0; i < 6; ++i) key.T[i] = T[i];
+  auto it = s->graphs.find(key);
+  if (it == s->graphs.end()) {                    // first sight: eager run, remember the key
+    s->graphs.emplace(key, nann_searcher::GraphVal());
+    return search_core(s, B, T, st, push);
+  }
+  if (it->second.exec == nullptr) {               // second sight: capture
+    cudaGraph_t graph = nullptr;
+    const uint64_t l0 = g_launches.load(std::memory_order_relaxed);
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+      cudaGetLastError();
+      return search_core(s, B, T, st, push);      // e.g. the legacy default stream cannot be captured
+    }
+    const nann_status rc = search_core(s, B, T, st, push);
+    const cudaError_t e = cudaStreamEndCapture(st, &graph);
+    if (rc != NANN_OK || e != cudaSuccess || !graph) {
+      cudaGetLastError();
+      if (graph) cudaGraphDestroy(graph);
+      s->graphs.erase(it);
+      NANN_TRY(rc);
+      return search_core(s, B, T, st, push);
+    }
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t ei = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ei != cudaSuccess || !exec) {
+      cudaGetLastError();
+      s->graphs.erase(it);
+      return search_core(s, B, T, st, push);
+    }
+    it->second.exec = exec;
+    it->second.kernels = g_launches.load(std::memory_order_relaxed) - l0;   // counted while capturing: this replay is paid for
+    NANN_CUDA(cudaGraphLaunch(exec, st));
+    return NANN_OK;
+  }
+  NANN_CUDA(cudaGraphLaunch(it->second.exec, st));
+  g_launches.fetch_add(it->second.kernels, std::memory_order_relaxed);      // nann_kernel_launch_count() counts kernels, not graphs
   return NANN_OK;
 }
 

@@ -431,3 +431,36 @@ def test_shard_group_failed_query_fails_everywhere(nb, oracle, world):
     for r in range(2):
         assert np.all(outs[r][2].cpu().numpy() == 3)
         assert np.all(outs[r][0].cpu().numpy() == -1)
+
+
+def test_small_batches_replay_a_cuda_graph_bit_identically(nb, world):
+    """batch <= 32 on a capturable stream: call 1 runs eagerly, call 2 captures the launch sequence into a CUDA graph,
+    later calls replay it.  Every call must return the oracle's ids and scores bit for bit, for different queries,
+    batch sizes and level_topn, in EXACT and TENSOR precision (the latter against its own eager result)."""
+    import torch
+    T = world["T"]
+    T2 = [max(t // 2, 8) for t in T]
+    se = nb.Searcher(world["ix"], world["scorer"], 8, T)
+    side = torch.cuda.Stream()
+    launches = []
+    for rep in range(5):
+        for B, Tq in ((1, T), (3, T), (1, T2)):
+            users = world["queries"][rep * 8:rep * 8 + B]
+            l0 = nb.launch_count()
+            got = se.search(users, Tq, stream=side)
+            launches.append(nb.launch_count() - l0)
+            want = _oracle_batch(world, users, Tq)
+            np.testing.assert_array_equal(got["ids"], want["ids"])
+            np.testing.assert_array_equal(got["scores"].view(np.uint32), want["scores"].view(np.uint32))
+            assert got["n_scored"].sum() == want["n_scored"]
+    assert len(set(launches)) == 1                      # replays are counted kernel by kernel, like eager calls
+    # tensor-core scorer: replayed == eager, bit for bit
+    world["scorer"].set_precision(nb.SCORER_TENSOR)
+    try:
+        users = world["queries"][:2]
+        runs = [se.search(users, T, stream=side) for _ in range(4)]
+        for r in runs[1:]:
+            np.testing.assert_array_equal(r["ids"], runs[0]["ids"])
+            np.testing.assert_array_equal(r["scores"].view(np.uint32), runs[0]["scores"].view(np.uint32))
+    finally:
+        world["scorer"].set_precision(nb.SCORER_EXACT)
