@@ -459,13 +459,16 @@ def run_b200(args, T, rank, world, local_rank):
                            "rows_scored_per_query": rows_.item() / n_eval})
             return rec, rows_.item() / n_eval
 
-        # (1) smallest uniform scale that holds the target
-        scales = None
-        for s_ in SCALES:
-            rec, _ = evaluate([s_] * 5)
-            scales = [s_] * 5
-            if cal_target is None or rec >= cal_target - RECALL_TOL:
-                break
+        # (1) smallest uniform scale that holds the target (no unsharded operating point to hold: plain T / world)
+        scales = [1.0] * 5
+        if cal_target is None:
+            evaluate(scales)
+        else:
+            for s_ in SCALES:
+                rec, _ = evaluate([s_] * 5)
+                scales = [s_] * 5
+                if rec >= cal_target - RECALL_TOL:
+                    break
         # (2) lower the beams one by one while the target still holds (each accepted step scores fewer rows)
         if cal_target is not None:
             improved = True
@@ -700,6 +703,7 @@ def run_b200(args, T, rank, world, local_rank):
         "stages_ms_per_step": {k2: v / args.steps for k2, v in prof["ms"].items()},
         "stage_share": {k2: (v / stage_tot if stage_tot else 0) for k2, v in prof["ms"].items()},
         "profile_pass_ms_per_step": prof_ms / args.steps,
+        "exchange_exposed_ms_per_step": (dev_ms - prof_ms) / args.steps if world > 1 else 0.0,
         "rows_scored_per_query": rows / (B * args.steps) * world,
         "rows_scored_per_query_per_shard": rows / (B * args.steps),
         "cpu_baseline": cpu,

@@ -23,12 +23,13 @@ constexpr int KB_D = 128;           // embedding width the tensor-core pass is b
 constexpr int KB_KC = 128;          // candidates kept per row between rounds
 constexpr int KB_CAP = 512;         // append buffer per row
 constexpr int KB_TN = 256;          // columns per tile (UMMA N)
-constexpr int KB_STRIP = 16;        // column tiles per work item
+constexpr int KB_STRIP = 64;        // column tiles per work item (A tile re-read once per item: 2% of the B traffic)
+constexpr int KB_QUEUE = 8;         // survivors a filter thread parks in shared memory before it reserves buffer slots
 constexpr int KB_THREADS = 320;     // warp 0 producer, warp 1 MMA, warps 2..9 filter epilogue
 constexpr int KB_A_BYTES = 32768;   // 128 rows x 128 k fp16
 constexpr int KB_B_BYTES = 65536;   // 256 rows x 128 k fp16
 constexpr int KB_HJ_SLOTS = 8;      // column-norm ring: the producer is at most 4 tiles ahead of the slowest epilogue thread
-constexpr int KB_SMEM_BYTES = 2 * KB_A_BYTES + 2 * KB_B_BYTES + KB_HJ_SLOTS * KB_TN * 4 + 1024;
+constexpr int KB_SMEM_BYTES = 2 * KB_A_BYTES + 2 * KB_B_BYTES + KB_HJ_SLOTS * KB_TN * 4 + KB_QUEUE * 256 * 8 + 1024;
 constexpr int KB_MAX_CAND = 96;     // n_cand limit of the refine kernel (cap + M at level 0 with M = 32)
 
 // ---- exact row norms: sq[r] = sum_k x[k]^2, sequential fmaf chain in k (the oracle's definition)
@@ -94,7 +95,8 @@ knn_filter_kernel(KnnArgs p) {
   uint8_t* sA = smem;                         // 2 x 32 KB
   uint8_t* sB = smem + 2 * KB_A_BYTES;        // 2 x 64 KB
   float* hj_s = (float*)(sB + 2 * KB_B_BYTES);                  // [KB_HJ_SLOTS][256] sq_j / 2 of the tile's columns
-  uint64_t* bars = (uint64_t*)(hj_s + KB_HJ_SLOTS * KB_TN);
+  uint2* queue = (uint2*)(hj_s + KB_HJ_SLOTS * KB_TN);          // [KB_QUEUE][256 filter threads] parked survivors
+  uint64_t* bars = (uint64_t*)(queue + KB_QUEUE * 256);
   uint32_t* tmem_slot = (uint32_t*)(bars + 16);
   enum { A_FULL = 0, A_EMPTY = 2, B_FULL = 4, B_EMPTY = 6, D_FULL = 8, D_EMPTY = 10 };
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -191,6 +193,21 @@ knn_filter_kernel(KnnArgs p) {
     const int ew = warp - 2, lane_q = warp & 3, col_half = ew >> 2;
     const uint32_t t_lane = (uint32_t)(lane_q * 32) << 16;
     uint32_t ib = 0;
+    // A survivor costs an atomicAdd on the row's counter, i.e. an L2 round trip (~1.5k cycles) that the whole warp waits
+    // for; with ~2 survivors per warp and tile that was 4x the MMA time of a tile (tensor pipe 19 % busy).  Survivors are
+    // parked in shared memory instead and the slots of all of them are reserved with ONE atomicAdd per thread at the end
+    // of the work item (or when the thread's queue is full: the first rounds, where everything survives).
+    uint2* my_q = queue + (tid - 64);
+    int n_q = 0;
+    auto flush = [&](int64_t lrow) {
+      if (n_q == 0) return;
+      const int slot0 = atomicAdd(p.cnt + lrow, n_q);
+      for (int e = 0; e < n_q; ++e) {
+        if (slot0 + e < KB_CAP) p.buf[lrow * KB_CAP + slot0 + e] = my_q[e * 256];
+        else atomicAdd(p.overflow, 1ull);
+      }
+      n_q = 0;
+    };
     for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x) {
       int rbi, ct0, nct;
       item_of(it, rbi, ct0, nct);
@@ -224,9 +241,9 @@ knn_filter_kernel(KnnArgs p) {
                 const int64_t j = c0 + g * 4 + e;
                 if (pp[e] && j != row) {
                   const float d2 = sqi + 2.0f * (hh[e] - __uint_as_float(v[g * 4 + e]));
-                  const int slot = atomicAdd(p.cnt + lrow, 1);
-                  if (slot < KB_CAP) p.buf[lrow * KB_CAP + slot] = make_uint2(__float_as_uint(d2), (uint32_t)j);
-                  else atomicAdd(p.overflow, 1ull);
+                  if (n_q == KB_QUEUE) flush(lrow);
+                  my_q[n_q * 256] = make_uint2(__float_as_uint(d2), (uint32_t)j);
+                  ++n_q;
                 }
               }
             }
@@ -235,6 +252,7 @@ knn_filter_kernel(KnnArgs p) {
         tc_fence_before();
         mbar_arrive(BAR(D_EMPTY + st));
       }
+      flush(lrow);
     }
   }
   __syncwarp();
