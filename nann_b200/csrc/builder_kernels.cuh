@@ -222,35 +222,48 @@ knn_filter_kernel(KnnArgs p) {
         const int64_t c_tile = p.col0 + (int64_t)(ct0 + t) * KB_TN + col_half * 128;
         const float* hj_t = hj_s + (ib % KB_HJ_SLOTS) * KB_TN + col_half * 128;
         const uint32_t tb = tmem + t_lane + st * 256 + (uint32_t)(col_half * 128);
-#pragma unroll 1
-        for (int ch = 0; ch < 4; ++ch) {
-          uint32_t v[32];
-          tc_ld32(tb + ch * 32, v);
-          const int64_t c0 = c_tile + ch * 32;
+        // One test per 32 columns instead of one per 4: t = max_c (dot_c - sq_c / 2) > h_i ?  (survivors are rare: ~128 per
+        // row and round).  The next 32 columns are already on their way from TMEM while these are reduced, and the
+        // accumulator is handed back to the MMA warp as soon as the last TMEM read has landed, not after the math.
+        uint32_t va[32], vb[32];
+        auto chunk = [&](uint32_t (&v)[32], uint32_t (&vnext)[32], int ch) {
+          tc_ld_wait_dep(v);
+          if (ch < 3) tc_ld32_nowait(tb + (ch + 1) * 32, vnext);
+          else { tc_fence_before(); mbar_arrive(BAR(D_EMPTY + st)); }
+          float4 h[8];
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const float4 h = *reinterpret_cast<const float4*>(hj_t + ch * 32 + g * 4);
-            // pass <=> tau > sq_i + sq_j - 2 dot  <=>  dot - sq_j/2 > (sq_i - tau)/2
-            const bool p0 = (__uint_as_float(v[g * 4 + 0]) - h.x) > hi, p1 = (__uint_as_float(v[g * 4 + 1]) - h.y) > hi;
-            const bool p2 = (__uint_as_float(v[g * 4 + 2]) - h.z) > hi, p3 = (__uint_as_float(v[g * 4 + 3]) - h.w) > hi;
-            if (p0 | p1 | p2 | p3) {
-              const float hh[4] = {h.x, h.y, h.z, h.w};
-              const bool pp[4] = {p0, p1, p2, p3};
+          for (int g = 0; g < 8; ++g) h[g] = *reinterpret_cast<const float4*>(hj_t + ch * 32 + g * 4);
+          float m[8];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int64_t j = c0 + g * 4 + e;
-                if (pp[e] && j != row) {
-                  const float d2 = sqi + 2.0f * (hh[e] - __uint_as_float(v[g * 4 + e]));
-                  if (n_q == KB_QUEUE) flush(lrow);
-                  my_q[n_q * 256] = make_uint2(__float_as_uint(d2), (uint32_t)j);
-                  ++n_q;
+          for (int g = 0; g < 8; ++g)
+            m[g] = fmaxf(fmaxf(__uint_as_float(v[g * 4 + 0]) - h[g].x, __uint_as_float(v[g * 4 + 1]) - h[g].y),
+                         fmaxf(__uint_as_float(v[g * 4 + 2]) - h[g].z, __uint_as_float(v[g * 4 + 3]) - h[g].w));
+          const float best = fmaxf(fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])), fmaxf(fmaxf(m[4], m[5]), fmaxf(m[6], m[7])));
+          if (best > hi) {               // pass <=> tau > sq_i + sq_j - 2 dot  <=>  dot - sq_j/2 > (sq_i - tau)/2
+            const int64_t c0 = c_tile + ch * 32;
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              if (m[g] > hi) {
+                const float hh[4] = {h[g].x, h[g].y, h[g].z, h[g].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float dot = __uint_as_float(v[g * 4 + e]);
+                  const int64_t j = c0 + g * 4 + e;
+                  if ((dot - hh[e]) > hi && j != row) {
+                    if (n_q == KB_QUEUE) flush(lrow);
+                    my_q[n_q * 256] = make_uint2(__float_as_uint(sqi + 2.0f * (hh[e] - dot)), (uint32_t)j);
+                    ++n_q;
+                  }
                 }
               }
             }
           }
-        }
-        tc_fence_before();
-        mbar_arrive(BAR(D_EMPTY + st));
+        };
+        tc_ld32_nowait(tb, va);
+        chunk(va, vb, 0);
+        chunk(vb, va, 1);
+        chunk(va, vb, 2);
+        chunk(vb, va, 3);
       }
       flush(lrow);
     }
