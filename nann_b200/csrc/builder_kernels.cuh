@@ -87,6 +87,24 @@ struct KnnArgs {
   unsigned long long* overflow;          // appends dropped because a row's buffer was full
 };
 
+// A survivor of the threshold test is parked in the thread's shared-memory queue; a full queue reserves its slots in
+// the row's buffer with ONE atomicAdd.  Deliberately not inlined: the filter loop has 128 call sites, and with the body
+// inlined the kernel grew to 470 KB of SASS -- rounds in which most 32-column chunks hold a survivor then ran out of the
+// instruction cache and the whole build got 2.8x slower.
+__device__ __noinline__ void knn_flush(uint2* my_q, int n_q, int* cnt, uint2* buf_row, unsigned long long* overflow) {
+  const int slot0 = atomicAdd(cnt, n_q);
+  for (int e = 0; e < n_q; ++e) {
+    if (slot0 + e < KB_CAP) buf_row[slot0 + e] = my_q[e * 256];
+    else atomicAdd(overflow, 1ull);
+  }
+}
+__device__ __noinline__ int knn_park(uint2* my_q, int n_q, uint32_t d2bits, uint32_t j, int* cnt, uint2* buf_row,
+                                     unsigned long long* overflow) {
+  if (n_q == KB_QUEUE) { knn_flush(my_q, n_q, cnt, buf_row, overflow); n_q = 0; }
+  my_q[n_q * 256] = make_uint2(d2bits, j);
+  return n_q + 1;
+}
+
 __global__ void __launch_bounds__(KB_THREADS, 1)
 knn_filter_kernel(KnnArgs p) {
   extern __shared__ uint8_t kb_smem[];
@@ -201,11 +219,7 @@ knn_filter_kernel(KnnArgs p) {
     int n_q = 0;
     auto flush = [&](int64_t lrow) {
       if (n_q == 0) return;
-      const int slot0 = atomicAdd(p.cnt + lrow, n_q);
-      for (int e = 0; e < n_q; ++e) {
-        if (slot0 + e < KB_CAP) p.buf[lrow * KB_CAP + slot0 + e] = my_q[e * 256];
-        else atomicAdd(p.overflow, 1ull);
-      }
+      knn_flush(my_q, n_q, p.cnt + lrow, p.buf + lrow * KB_CAP, p.overflow);
       n_q = 0;
     };
     for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x) {
@@ -249,11 +263,9 @@ knn_filter_kernel(KnnArgs p) {
                 for (int e = 0; e < 4; ++e) {
                   const float dot = __uint_as_float(v[g * 4 + e]);
                   const int64_t j = c0 + g * 4 + e;
-                  if ((dot - hh[e]) > hi && j != row) {
-                    if (n_q == KB_QUEUE) flush(lrow);
-                    my_q[n_q * 256] = make_uint2(__float_as_uint(sqi + 2.0f * (hh[e] - dot)), (uint32_t)j);
-                    ++n_q;
-                  }
+                  if ((dot - hh[e]) > hi && j != row)
+                    n_q = knn_park(my_q, n_q, __float_as_uint(sqi + 2.0f * (hh[e] - dot)), (uint32_t)j, p.cnt + lrow,
+                                   p.buf + lrow * KB_CAP, p.overflow);
                 }
               }
             }
