@@ -757,7 +757,11 @@ static nann_status search_core(nann_searcher* s, int B, const int32_t T[6], cuda
     a.k = k; a.out_sc = s->out_sc; a.out_ids = s->out_nodes; a.out_stride = std::max(k, 1);
     a.item_ids = ix->item_ids; a.out_item_ids = s->out_item; a.out_item_stride = std::max(k, 1);
     a.status = s->status;
-    if (push) a.push = *push;
+    if (push) {
+      a.push = *push;
+      if (push->need_done > 0)
+        NANN_LAUNCH(shard_backpressure_kernel, 1, 32, 0, st, push->my_done, push->world, push->need_done, push->error);
+    }
     NANN_TRY(topk_timed(a));
   }
   return NANN_OK;

@@ -664,17 +664,13 @@ topk_kernel(TopkArgs a) {
   topk_row(a, row, sel);
   if (a.push.world == 0) return;
   // ---- shard exchange epilogue: this query's records -> every rank's window, then the delivery flags
+  // (the window slot is free: shard_backpressure_kernel ran before this kernel.  The wait is NOT done here: CTAs that
+  // spin on the peers' done flags while they fill every SM would keep this GPU's own merge kernel -- which produces one
+  // of those flags -- from ever being scheduled.)
   const ShardPush& P = a.push;
   const int tid = threadIdx.x;
-  __shared__ int s_ok;
-  if (tid == 0) {            // the slot must have been merged by everyone `depth` sequences ago
-    bool ok = true;
-    for (int p = 0; p < P.world && ok; ++p) ok = shard_wait_flag(P.my_done + p, P.need_done);
-    if (!ok) *P.error = 1;
-    s_ok = ok ? 1 : 0;
-  }
-  __syncthreads();           // also orders the emit loop's writes before the re-reads below (same thread anyway)
-  if (s_ok) {
+  __syncthreads();           // orders the emit loop's writes before the re-reads below (same thread anyway)
+  {
     const int32_t st = a.status ? a.status[row] : 0;
     for (int r = tid; r < P.k; r += TOPK_THREADS) {
       const float sc = st == 0 ? a.out_sc[row * a.out_stride + a.out_offset + r] : __int_as_float(-1);
@@ -755,6 +751,12 @@ shard_merge_kernel(ShardMergeArgs a) {
       for (int p = 0; p < a.world; ++p) st_release_sys_u64(a.done[p], a.seq + 1);
     }
   }
+}
+// one warp, before the final top-k of a sharded search: lane p waits until rank p has merged the sequence that used
+// this window slot before (done[p] >= need_done), so that the push may overwrite it
+__global__ void shard_backpressure_kernel(const unsigned long long* my_done, int world, unsigned long long need_done, int* error) {
+  const int p = threadIdx.x;
+  if (p < world && !shard_wait_flag(my_done + p, need_done)) *error = 1;
 }
 // one warp: lane p waits for shard p's delivery of `seq` into this rank's window slot
 __global__ void shard_wait_kernel(const unsigned long long* arrive, int world, unsigned long long seq, int* error) {
