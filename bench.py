@@ -414,7 +414,7 @@ def run_b200(args, T, rank, world, local_rank):
         return m_id, m_sc, st_
 
     recall_target = None
-    if world > 1 and truth is not None and args.shard_scale <= 0:
+    if world > 1 and truth is not None and args.shard_scale <= 0 and not args.shard_scales:
         from nann_b200 import distributed as nd
         # a second, independent query set drives the calibration; the recall that is REPORTED (and checked against the
         # one-GPU operating point) is measured on eval_q afterwards
@@ -495,8 +495,9 @@ def run_b200(args, T, rank, world, local_rank):
         extra["calibration"] = trials
         del cal_dev
     elif world > 1:
-        scale = args.shard_scale if args.shard_scale > 0 else 1.0
-        Ts = shard_topn(T, world, scale)
+        from nann_b200 import distributed as nd
+        scale = [float(x) for x in args.shard_scales.split(",")] if args.shard_scales else [args.shard_scale if args.shard_scale > 0 else 1.0] * 5
+        Ts = nd.shard_beams(T, world, scale)
 
     se = nb.Searcher(ix, sc, B, Ts)
     k_s = Ts[5]
@@ -657,6 +658,25 @@ def run_b200(args, T, rank, world, local_rank):
                 cpu["exact_path_scores_bit_equal"] = bool(np.array_equal(ex["scores"].view(np.uint32), r["scores"].view(np.uint32)))
         except Exception as e:
             cpu = {"error": repr(e)[:200]}
+    if rank == 0 and world > 1 and args.cpu_shard_sample > 0:
+        # the CPU port on ONE shard of the sharded corpus (rank 0's rows, the per-shard beams): a whole query costs the
+        # host `world` of these, so queries/s of the CPU port on the full corpus = this / world
+        try:
+            from oracle import oracle as orc
+            cores = os.cpu_count() or 1
+            oix = orc.Index(sh["emb"], sh["item_ids"], sh["ep"].astype(np.int32), [v.astype(np.int32) for v in sh["values"]], sh["row_splits"])
+            om = orc.Mlp(*sw.mlp_weights(seed=3))
+            nq = args.cpu_shard_sample
+            r = oix.search_batch_mlp(om, queries[:nq], Ts, nthreads=cores)
+            mine = se.search(queries[:nq], Ts)
+            extra["cpu_port_one_shard"] = {
+                "shard_searches_per_s": nq / r["seconds"], "queries_per_s_full_corpus": nq / r["seconds"] / world, "cores": cores,
+                "sample": f"{nq} queries against rank 0's {len(sh['item_ids'])}-row shard with the per-shard beams, one request per core, {r['seconds']:.1f}s",
+                "rows_scored_per_shard_search": r["n_scored"] / nq,
+                "topk_overlap_with_gpu_shard_search": float(np.mean([len(set(a.tolist()) & set(b.tolist())) / max(Ts[5], 1)
+                                                                      for a, b in zip(mine["ids"], r["ids"])]))}
+        except Exception as e:
+            extra["cpu_port_one_shard"] = {"error": repr(e)[:200]}
     if grp is not None:
         barrier()
         grp.close()
@@ -753,6 +773,9 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("NANN_BENCH_PRECISION", "tensor"), choices=["exact", "tensor"])
     ap.add_argument("--eval-queries", type=int, default=128, help="queries of the recall@k measurement / calibration")
     ap.add_argument("--shard-scale", type=float, default=0.0, help="N>1: fix the per-shard beam scale instead of calibrating it")
+    ap.add_argument("--shard-scales", default="", help="N>1: five comma-separated per-beam scales (e.g. the ones a smaller corpus calibrated to)")
+    ap.add_argument("--cpu-shard-sample", type=int, default=0,
+                    help="N>1: rank 0 also times the CPU port on ITS shard with the per-shard beams for this many queries")
     ap.add_argument("--no-replica", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
