@@ -134,7 +134,8 @@ def build_graph(emb, seed, device):
     if builder_name(device) == "cuda-builder":
         from nann_b200 import builder
         dev_index = int(str(device).split(":")[1]) if ":" in str(device) else 0
-        return builder.build_hnsw(emb, M=32, start_level=2, seed=seed, device=dev_index)
+        return builder.build_hnsw(emb, M=32, start_level=2, seed=seed, device=dev_index,
+                                  values_dtype=np.int32 if emb.shape[0] > 4_000_000 else np.int64)
     return nix().build_hnsw(emb, M=32, start_level=2, seed=seed, device=device)
 
 

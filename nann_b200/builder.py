@@ -16,8 +16,10 @@ class BuildStats(C.Structure):
                 ("n_overflow", C.c_int64)]
 
 
-def build_hnsw(emb, M=32, start_level=2, m_levels=None, seed=4, device=0, levels=None, return_stats=False):
-    """emb: float32 [n, 128] numpy array or CUDA tensor.  m_levels: base of the level distribution (default M)."""
+def build_hnsw(emb, M=32, start_level=2, m_levels=None, seed=4, device=0, levels=None, return_stats=False, values_dtype=np.int64):
+    """emb: float32 [n, 128] numpy array or CUDA tensor.  m_levels: base of the level distribution (default M).
+    values_dtype: int64 like the files build_hnsw_index.py writes, or int32 (what build_opt_graph.py casts them to;
+    half the host memory for a 12.5M-row shard)."""
     is_torch = type(emb).__module__.startswith("torch")
     if is_torch:
         e = emb.contiguous().float()
@@ -44,7 +46,7 @@ def build_hnsw(emb, M=32, start_level=2, m_levels=None, seed=4, device=0, levels
                                   C.c_void_p, C.c_void_p]
     check(L.nann_hnsw_build(ptr, n, d, C.c_void_p(lv.ctypes.data), int(M), int(start_level), int(device), cb, None, C.byref(st)))
     out = {"enter_points": np.nonzero(lv + 1 > start_level)[0].astype(np.int64), "levels": lv,
-           "values": [outs[2 * l].astype(np.int64) for l in range(start_level)],
+           "values": [outs[2 * l].astype(values_dtype, copy=False) for l in range(start_level)],
            "row_splits": [outs[2 * l + 1] for l in range(start_level)]}
     if return_stats:
         out["stats"] = dict(seconds_knn=st.seconds_knn, seconds_links=st.seconds_links, n_forward_links=st.n_forward_links,
