@@ -366,6 +366,34 @@ nann_status nann_search_sharded_merge(nann_shard_group_t* g, int k_out, int64_t*
 nann_status nann_shard_group_wait(nann_shard_group_t* g, void* stream, int host_block);
 
 /* ------------------------------------------------------------------------------------------
+ * Distributed scoring: the second multi-GPU form (csrc/lib_dist.inl).  ONE graph (replicated, like the enter points
+ * and item ids), the embedding table row-sharded -- rank r of `world` holds rows [r*per, (r+1)*per), per =
+ * ceil(n_items / world), nann_index_create_sharded -- and the global batch partitioned: every rank runs the
+ * traversal of ITS B queries; each scoring round the candidates are sent to the ranks that own their rows, scored there
+ * with the ordinary scorer kernel, and the scores come back (stores into IPC-mapped peer windows over NVLink + flags,
+ * no host synchronisation).  The result is BIT-IDENTICAL to nann_search_batch on the unsharded index; per-GPU scoring
+ * work is 1/world of it.  Every rank must call nann_search_distributed with the same B and level_topn (collective);
+ * out_* are this rank's queries only.  mlp scorer only.  Device outputs: the call only enqueues on `stream`
+ * (nann_dist_group_check reports a timed-out exchange); host outputs: it returns when they are filled -- every rank
+ * then needs its own thread or process.
+ * ---------------------------------------------------------------------------------------- */
+nann_status nann_index_create_sharded(int64_t n_items, int dim, const void* emb_rows, int emb_dtype, int64_t row_lo,
+                                      int64_t n_rows_local, const int64_t* item_ids, const void* enter_points,
+                                      int ep_dtype, int64_t n_enter_points, const void* const nbr_values[2],
+                                      const int64_t n_nbr_values[2], int nbr_dtype,
+                                      const int64_t* const nbr_row_splits[2], int device, nann_index_t** out);
+typedef struct nann_dist_group nann_dist_group_t;
+nann_status nann_dist_group_create(const nann_searcher_t* s, int rank, int world, nann_dist_group_t** out);
+nann_status nann_dist_group_export(nann_dist_group_t* g, void* handle);   /* nann_shard_group_handle_bytes() bytes */
+nann_status nann_dist_group_connect(nann_dist_group_t* g, const void* handles);
+nann_status nann_dist_group_connect_local(nann_dist_group_t* const* members, int world);
+nann_status nann_dist_group_check(nann_dist_group_t* g);
+void nann_dist_group_destroy(nann_dist_group_t* g);
+nann_status nann_search_distributed(nann_searcher_t* s, nann_dist_group_t* g, const float* users, int B,
+                                    const int32_t level_topn[6], int64_t* out_item_ids, float* out_scores,
+                                    int32_t* out_status, nann_search_stats_t* stats, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Index construction.  The reference builds its graph offline with faiss
  * IndexHNSWFlat(d, M) and dumps per-level CSR files (NANN_impls/nann/delivery/build_hnsw_index.py:33-67);
  * this builds the same FILES on the GPU: per level l < n_levels the links of the nodes whose level reaches l

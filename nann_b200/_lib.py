@@ -111,6 +111,15 @@ def lib():
     L.nann_shard_group_wait.argtypes = [vp, vp, i32]
     L.nann_search_sharded_push.argtypes = [vp, vp, vp, i32, vp, vp]
     L.nann_search_sharded_merge.argtypes = [vp, i32, vp, vp, vp]
+    L.nann_index_create_sharded.argtypes = [i64, i32, vp, i32, i64, i64, vp, vp, i32, i64, vp, vp, i32, vp, i32, vp]
+    L.nann_dist_group_create.argtypes = [vp, i32, i32, vp]
+    L.nann_dist_group_export.argtypes = [vp, vp]
+    L.nann_dist_group_connect.argtypes = [vp, vp]
+    L.nann_dist_group_connect_local.argtypes = [vp, i32]
+    L.nann_dist_group_check.argtypes = [vp]
+    L.nann_dist_group_destroy.restype = None
+    L.nann_dist_group_destroy.argtypes = [vp]
+    L.nann_search_distributed.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp, vp, vp]
     L.nann_eval_searcher_create.argtypes = [vp, vp, i32, vp, i32, vp]
     L.nann_eval_searcher_destroy.restype = None
     L.nann_eval_searcher_destroy.argtypes = [vp]

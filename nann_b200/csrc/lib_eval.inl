@@ -216,6 +216,7 @@ nann_status nann_eval_searcher_create(const nann_index_t* ix, nann_scorer_t* sco
   if (max_batch > 65535) return fail(NANN_UNIMPLEMENTED, "max_batch > 65535");
   if (nann_scorer_item_dim(scorer) != ix->dim)
     return fail(NANN_INVALID_ARGUMENT, "scorer item dim %d != index dim %d", nann_scorer_item_dim(scorer), ix->dim);
+  if (ix->n_local != ix->n_items) return fail(NANN_FAILED_PRECONDITION, "the index holds a slice of the table only");
   NANN_CUDA(cudaSetDevice(ix->device));
   auto* s = new nann_eval_searcher();
   s->ix = ix; s->sc = scorer; s->max_batch = max_batch;

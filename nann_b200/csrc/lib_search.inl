@@ -79,7 +79,8 @@ struct nann_index {
   int device = 0;
   int64_t n_items = 0;
   int dim = 0;
-  float* emb = nullptr;        // [n_items][dim] f32
+  float* emb = nullptr;        // [n_local][dim] f32: rows row_lo .. row_lo + n_local of the table (all of it unless sharded)
+  int64_t row_lo = 0, n_local = 0;
   int64_t* item_ids = nullptr; // [n_items]
   int32_t* ep = nullptr;       // [n_ep]
   int64_t n_ep = 0;
@@ -365,28 +366,39 @@ nann_status nann_index_create(int64_t n_items, int dim, const void* emb, int emb
                               const int64_t* item_ids, const void* enter_points, int ep_dtype,
                               int64_t n_ep, const void* const nbr_values[2], const int64_t n_nbr_values[2],
                               int nbr_dtype, const int64_t* const nbr_row_splits[2], int device, nann_index_t** out) {
+  return nann_index_create_sharded(n_items, dim, emb, emb_dtype, 0, n_items, item_ids, enter_points, ep_dtype, n_ep,
+                                   nbr_values, n_nbr_values, nbr_dtype, nbr_row_splits, device, out);
+}
+
+nann_status nann_index_create_sharded(int64_t n_items, int dim, const void* emb, int emb_dtype, int64_t row_lo, int64_t n_local,
+                                      const int64_t* item_ids, const void* enter_points, int ep_dtype,
+                                      int64_t n_ep, const void* const nbr_values[2], const int64_t n_nbr_values[2],
+                                      int nbr_dtype, const int64_t* const nbr_row_splits[2], int device, nann_index_t** out) {
   if (!out) return fail(NANN_INVALID_ARGUMENT, "null out");
   *out = nullptr;
   NANN_TRY(require_device());
   if (n_items <= 0 || dim <= 0 || !emb || !item_ids || !enter_points || !nbr_values || !n_nbr_values || !nbr_row_splits)
     return fail(NANN_INVALID_ARGUMENT, "nann_index_create: null or empty input");
   if (n_items > 0x7fffffffll) return fail(NANN_UNIMPLEMENTED, "n_items > 2^31-1 per shard");
+  if (row_lo < 0 || n_local <= 0 || row_lo + n_local > n_items)
+    return fail(NANN_INVALID_ARGUMENT, "table rows [%lld, %lld) outside [0, %lld)", (long long)row_lo, (long long)(row_lo + n_local), (long long)n_items);
   NANN_CUDA(cudaSetDevice(device));
   cudaStream_t st = 0;
   auto* ix = new nann_index();
   ix->device = device; ix->n_items = n_items; ix->dim = dim; ix->n_ep = n_ep;
+  ix->row_lo = row_lo; ix->n_local = n_local;
   DevBuf<int> flags;  // [0]=bad ids, [1]=bad csr, [2]=ep order, [3..4]=max degree
   nann_status rc = flags.alloc(8);
   auto step = [&](nann_status r) { if (rc == NANN_OK) rc = r; return rc == NANN_OK; };
   if (rc == NANN_OK) cudaMemsetAsync(flags.d, 0, 8 * sizeof(int), st);
   if (rc == NANN_OK) {
-    if (emb_dtype == NANN_F32) step(to_device_copy((const float*)emb, n_items * dim, &ix->emb, st));
+    if (emb_dtype == NANN_F32) step(to_device_copy((const float*)emb, n_local * dim, &ix->emb, st));
     else if (emb_dtype == NANN_F16) {  // widened once in memory (never on disk)
       DevIn<__half> h;
-      if (step(h.init((const __half*)emb, n_items * dim, st)) &&
-          step(cudaMalloc(&ix->emb, (size_t)n_items * dim * 4) == cudaSuccess ? NANN_OK
+      if (step(h.init((const __half*)emb, n_local * dim, st)) &&
+          step(cudaMalloc(&ix->emb, (size_t)n_local * dim * 4) == cudaSuccess ? NANN_OK
                    : fail(NANN_RESOURCE_EXHAUSTED, "OOM for item_embs"))) {
-        NANN_LAUNCH(f16_to_f32_kernel, 148 * 8, 256, 0, st, h.d, ix->emb, n_items * dim);
+        NANN_LAUNCH(f16_to_f32_kernel, 148 * 8, 256, 0, st, h.d, ix->emb, n_local * dim);
         cudaStreamSynchronize(st);
       }
     } else rc = fail(NANN_INVALID_ARGUMENT, "item_embs must be f16 or f32");
@@ -487,7 +499,9 @@ void nann_index_destroy(nann_index_t* ix) {
 }  // extern "C"
 
 // ---- searcher ------------------------------------------------------------------------------------
+struct nann_dist_group;   // lib_dist.inl
 struct nann_searcher {
+  nann_dist_group* dist = nullptr;   // set for the duration of a nann_search_distributed call
   const nann_index* ix = nullptr;
   nann_scorer* sc = nullptr;
   int max_batch = 0;
@@ -611,6 +625,10 @@ namespace nann {
 // the searcher's out_sc / out_nodes / out_item ([B][max(k,1)]), per-query status and the per-round counters in
 // s->status / s->round_n / s->round_exp.  `push` (optional) makes the final top-k deliver its records to the shard
 // group's windows as well (lib_shard.inl).
+static nann_status dist_share_user_state(nann_dist_group* g, const float* ustate, int B, cudaStream_t st);
+static nann_status dist_score_round(nann_searcher* s, nann_dist_group* g, const int32_t* ids, int64_t ids_stride, const int32_t* n_ptr,
+                                    int n_fixed, int64_t bound, int B, cudaStream_t st);
+
 __global__ void copy_floats_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[i];
 }
@@ -632,6 +650,7 @@ static nann_status search_core(nann_searcher* s, int B, const int32_t T[6], cuda
     NANN_LAUNCH(search_init_kernel, (unsigned)std::min<int64_t>(ceil_div(work, 256), 148 * 4), 256, 0, st, ia);
   }
   NANN_TRY(scorer_prepare_users(s->sc, s->users, B, s->ustate, st));
+  if (s->dist) NANN_TRY(dist_share_user_state(s->dist, s->ustate, B, st));
 
   s->ev_used = 0;
   auto t_begin = [&](int stage) {
@@ -658,7 +677,8 @@ static nann_status search_core(nann_searcher* s, int B, const int32_t T[6], cuda
     if (!s->tcws) s->tcws = new nann::TcWorkspace();
     c.ws = s->tcws;
     t_begin(0);
-    nann_status rc_score = scorer_score(s->sc, c, st);
+    nann_status rc_score = s->dist ? dist_score_round(s, s->dist, ids, ids_stride, n_ptr, n_fixed, bound, B, st)
+                                   : scorer_score(s->sc, c, st);
     t_end();
     NANN_TRY(rc_score);
     if (s->trace) {
@@ -780,7 +800,7 @@ static nann_status search_enqueue(nann_searcher* s, const float* users, int B, c
     NANN_CUDA(cudaMemcpyAsync(s->users, users, (size_t)B * uf * 4, cudaMemcpyHostToDevice, st));
   s->last_B = B; s->last_k = T[5];
   static const int graph_max_b = [] { const char* e = std::getenv("NANN_GRAPH_MAX_BATCH"); return e ? atoi(e) : 32; }();
-  if (push || s->trace || s->profile || B > graph_max_b) return search_core(s, B, T, st, push);
+  if (push || s->dist || s->trace || s->profile || B > graph_max_b) return search_core(s, B, T, st, push);
   nann_searcher::GraphKey key{};
   key.B = B; key.precision = s->sc->precision;
   for (int i = 0; i < 6; ++i) key.T[i] = T[i];
@@ -840,36 +860,12 @@ static void search_collect_profile(nann_searcher* s, int B) {
     for (int r = 1; r < 5; ++r) s->prof_rows += s->h_round_n[(size_t)r * mb + q];
 }
 
-static nann_status search_check_args(nann_searcher* s, const float* users, int B, const int32_t T[6]) {
-  if (!s || !users || !T) return fail(NANN_INVALID_ARGUMENT, "nann_search_batch: null argument");
-  if (B < 0 || B > s->max_batch) return fail(NANN_INVALID_ARGUMENT, "batch %d outside [0, %d]", B, s->max_batch);
-  for (int i = 0; i < 6; ++i) {
-    if (T[i] < 0) return fail(NANN_INVALID_ARGUMENT, "Need k >= 0, got %d", T[i]);  // topk_op.cc:60-61
-    if (T[i] > s->maxT[i]) return fail(NANN_INVALID_ARGUMENT, "level_topn[%d]=%d exceeds the searcher's maximum %d", i, T[i], s->maxT[i]);
-  }
-  return NANN_OK;
-}
-
-}  // namespace nann
-
-extern "C" {
-
-nann_status nann_search_batch(nann_searcher_t* s, const float* users, int B, const int32_t T[6],
-                              int64_t* out_item_ids, float* out_scores, int32_t* out_status,
-                              nann_search_stats_t* stats, void* stream) {
-  NANN_TRY(require_device());
-  NANN_TRY(search_check_args(s, users, B, T));
-  if (stats) memset(stats, 0, sizeof(*stats));
-  if (B == 0) return NANN_OK;
+// results of the last enqueue -> caller.  All-device outputs and nothing the host has to look at (stats, profile):
+// asynchronous, the caller orders later work on `st`; otherwise the call synchronises.
+static nann_status search_deliver(nann_searcher* s, int B, int k, int64_t* out_item_ids, float* out_scores, int32_t* out_status,
+                                  nann_search_stats_t* stats, cudaStream_t st) {
   const nann_index* ix = s->ix;
-  cudaStream_t st = (cudaStream_t)stream;
-  NANN_CUDA(cudaSetDevice(ix->device));
   const int64_t mb = s->max_batch;
-  const int k = T[5];
-  NANN_TRY(search_enqueue(s, users, B, T, st, nullptr));
-
-  // ---- results back.  All-device outputs and nothing the host has to look at (stats, profile): asynchronous, the
-  // caller orders later work on `stream`; otherwise the call synchronises.
   const bool dev_ids = !out_item_ids || is_device_ptr(out_item_ids), dev_sc = !out_scores || is_device_ptr(out_scores);
   const bool dev_st = !out_status || is_device_ptr(out_status);
   if (k > 0) {
@@ -902,6 +898,40 @@ nann_status nann_search_batch(nann_searcher_t* s, const float* users, int B, con
     stats->n_expanded[0] = (int64_t)B * ix->n_ep;
   }
   return NANN_OK;
+}
+
+static nann_status search_check_args(nann_searcher* s, const float* users, int B, const int32_t T[6]) {
+  if (!s || !users || !T) return fail(NANN_INVALID_ARGUMENT, "nann_search_batch: null argument");
+  if (B < 0 || B > s->max_batch) return fail(NANN_INVALID_ARGUMENT, "batch %d outside [0, %d]", B, s->max_batch);
+  for (int i = 0; i < 6; ++i) {
+    if (T[i] < 0) return fail(NANN_INVALID_ARGUMENT, "Need k >= 0, got %d", T[i]);  // topk_op.cc:60-61
+    if (T[i] > s->maxT[i]) return fail(NANN_INVALID_ARGUMENT, "level_topn[%d]=%d exceeds the searcher's maximum %d", i, T[i], s->maxT[i]);
+  }
+  return NANN_OK;
+}
+
+}  // namespace nann
+
+extern "C" {
+
+nann_status nann_search_batch(nann_searcher_t* s, const float* users, int B, const int32_t T[6],
+                              int64_t* out_item_ids, float* out_scores, int32_t* out_status,
+                              nann_search_stats_t* stats, void* stream) {
+  NANN_TRY(require_device());
+  NANN_TRY(search_check_args(s, users, B, T));
+  if (s->ix->n_local != s->ix->n_items)
+    return fail(NANN_FAILED_PRECONDITION, "this index holds rows [%lld, %lld) of the table only: use nann_search_distributed",
+                (long long)s->ix->row_lo, (long long)(s->ix->row_lo + s->ix->n_local));
+  if (stats) memset(stats, 0, sizeof(*stats));
+  if (B == 0) return NANN_OK;
+  const nann_index* ix = s->ix;
+  cudaStream_t st = (cudaStream_t)stream;
+  NANN_CUDA(cudaSetDevice(ix->device));
+  const int64_t mb = s->max_batch;
+  const int k = T[5];
+  NANN_TRY(search_enqueue(s, users, B, T, st, nullptr));
+
+  return search_deliver(s, B, k, out_item_ids, out_scores, out_status, stats, st);
 }
 
 nann_status nann_searcher_get_trace(nann_searcher_t* s, int q, int round, int32_t* ids, float* scores,

@@ -166,6 +166,7 @@ nann_status nann_search_sharded_push(nann_searcher_t* s, nann_shard_group_t* g, 
   if (!g->connected) return fail(NANN_FAILED_PRECONDITION, "shard group is not connected (nann_shard_group_connect)");
   if (g->pending) return fail(NANN_FAILED_PRECONDITION, "a pushed search is waiting for nann_search_sharded_merge");
   if (s->ix->device != g->device) return fail(NANN_INVALID_ARGUMENT, "searcher is on device %d, shard group on %d", s->ix->device, g->device);
+  if (s->ix->n_local != s->ix->n_items) return fail(NANN_FAILED_PRECONDITION, "the index holds a slice of the table only: use nann_search_distributed");
   const int k_s = T[5];
   if (B > g->max_batch || k_s > g->max_k) return fail(NANN_INVALID_ARGUMENT, "batch %d / k %d exceed the group's window (%d / %d)", B, k_s, g->max_batch, g->max_k);
   if (B == 0) return NANN_OK;          // every rank sees the same B, so every rank skips the sequence

@@ -18,6 +18,7 @@
 #include "lib_ragged.inl"
 #include "lib_search.inl"
 #include "lib_shard.inl"
+#include "lib_dist.inl"
 #include "builder_kernels.cuh"
 #include "lib_builder.inl"
 #include "lib_bloom.inl"

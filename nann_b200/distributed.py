@@ -206,6 +206,89 @@ class ShardGroup:
             pass
 
 
+class DistGroup:
+    """This rank's end of DISTRIBUTED SCORING (nann_dist_group_t, csrc/lib_dist.inl): one graph, the embedding table
+    row-sharded, every rank traverses its own queries and scores the candidates it owns for everybody.  Results are
+    bit-identical to a one-GPU search of the unsharded index."""
+
+    def __init__(self, searcher, rank, world):
+        from . import _lib
+        self._lib = _lib
+        self.rank, self.world, self.searcher = int(rank), int(world), searcher
+        h = C.c_void_p()
+        _lib.check(_lib.lib().nann_dist_group_create(searcher._h, self.rank, self.world, C.byref(h)))
+        self._h = h
+
+    def export_handle(self):
+        n = self._lib.lib().nann_shard_group_handle_bytes()
+        buf = (C.c_ubyte * n)()
+        self._lib.check(self._lib.lib().nann_dist_group_export(self._h, buf))
+        return bytes(buf)
+
+    def connect(self, handles):
+        blob = b"".join(handles)
+        buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        self._lib.check(self._lib.lib().nann_dist_group_connect(self._h, buf))
+
+    def connect_torch(self, group=None):
+        import torch.distributed as dist
+        handles = [None] * self.world
+        dist.all_gather_object(handles, self.export_handle(), group=group)
+        self.connect(handles)
+        dist.barrier(group=group)
+
+    @staticmethod
+    def connect_local(members):
+        from . import _lib
+        arr = (C.c_void_p * len(members))(*[m._h for m in members])
+        _lib.check(_lib.lib().nann_dist_group_connect_local(arr, len(members)))
+
+    def search(self, users, level_topn, out_ids=None, out_scores=None, out_status=None, stream=None, want_stats=False):
+        """this rank's queries ([B, user_floats], the same B on every rank).  CUDA outputs: enqueue only (check()
+        afterwards); no outputs given: host arrays are returned and the call blocks."""
+        from . import ops
+        se = self.searcher
+        uf = se.scorer.user_floats
+        if ops._is_torch(users):
+            u = users.contiguous().float().reshape(-1, uf)
+            B, uptr = u.shape[0], C.c_void_p(u.data_ptr())
+        else:
+            u = np.ascontiguousarray(users, np.float32).reshape(-1, uf)
+            B, uptr = u.shape[0], C.c_void_p(u.ctypes.data)
+        T = (C.c_int32 * 6)(*[int(t) for t in level_topn])
+        k = max(int(level_topn[5]), 0)
+        if out_ids is None:
+            out_ids, out_scores, out_status = np.empty((B, k), np.int64), np.empty((B, k), np.float32), np.empty(B, np.int32)
+            ptrs = [C.c_void_p(a.ctypes.data) for a in (out_ids, out_scores, out_status)]
+        else:
+            _check_out(out_ids, "int64", (B, k)); _check_out(out_scores, "float32", (B, k))
+            if out_status is not None:
+                _check_out(out_status, "int32", (B,))
+            ptrs = [C.c_void_p(out_ids.data_ptr()), C.c_void_p(out_scores.data_ptr()),
+                    C.c_void_p(out_status.data_ptr()) if out_status is not None else None]
+        st = self._lib.SearchStats() if want_stats else None
+        self._lib.check(self._lib.lib().nann_search_distributed(se._h, self._h, uptr, B, T, ptrs[0], ptrs[1], ptrs[2],
+                                                                C.byref(st) if st is not None else None, ops._stream_ptr(stream)))
+        self._keep = u
+        if want_stats:
+            return out_scores, out_ids, out_status, dict(n_scored=np.array(st.n_scored[:], np.int64), n_failed=int(st.n_failed))
+        return out_scores, out_ids, out_status
+
+    def check(self):
+        self._lib.check(self._lib.lib().nann_dist_group_check(self._h))
+
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._lib.lib().nann_dist_group_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def _check_out(t, dtype, shape):
     if not (hasattr(t, "is_cuda") and t.is_cuda and t.is_contiguous() and str(t.dtype).endswith(dtype) and tuple(t.shape) == tuple(shape)):
         raise TypeError(f"output must be a contiguous CUDA {dtype} tensor of shape {tuple(shape)}")

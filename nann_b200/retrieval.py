@@ -59,6 +59,26 @@ class Index:
         return cls(h)
 
     @classmethod
+    def from_arrays_sharded(cls, n_items, emb_rows, row_lo, item_ids, enter_points, nbr_values, nbr_row_splits, device=0):
+        """Index for distributed scoring (nann_index_create_sharded): the graph, enter points and item ids of the WHOLE
+        corpus, but only rows [row_lo, row_lo + len(emb_rows)) of the embedding table (numpy arrays)."""
+        emb = np.ascontiguousarray(emb_rows)
+        if emb.dtype not in (np.dtype("float32"), np.dtype("float16")):
+            raise TypeError("item_embs must be float32 or float16")
+        ep = np.ascontiguousarray(enter_points)
+        vals_np = [np.ascontiguousarray(v) for v in nbr_values]
+        rs_np = [np.ascontiguousarray(r, np.int64) for r in nbr_row_splits]
+        ids = np.ascontiguousarray(item_ids, np.int64)
+        vals = (C.c_void_p * 2)(vals_np[0].ctypes.data, vals_np[1].ctypes.data)
+        rss = (C.c_void_p * 2)(rs_np[0].ctypes.data, rs_np[1].ctypes.data)
+        n_vals = (C.c_int64 * 2)(vals_np[0].size, vals_np[1].size)
+        h = C.c_void_p()
+        check(_lib.lib().nann_index_create_sharded(int(n_items), emb.shape[1], C.c_void_p(emb.ctypes.data), _NP2CODE[emb.dtype], int(row_lo),
+                                                   emb.shape[0], C.c_void_p(ids.ctypes.data), C.c_void_p(ep.ctypes.data), _NP2CODE[ep.dtype],
+                                                   ep.size, vals, n_vals, _NP2CODE[vals_np[0].dtype], rss, int(device), C.byref(h)))
+        return cls(h)
+
+    @classmethod
     def load(cls, embs_dir, index_dir, device=0):
         """item_embs.npy / item_ids.npy from embs_dir; enter_points.npy and
         neighbors_level_{0,1}_{values,row_splits}.npy from index_dir (either dtype width)."""

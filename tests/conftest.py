@@ -3,6 +3,9 @@ import sys
 
 import pytest
 
+# one hardware work queue per stream: tests that drive several group members from one process keep a flag-waiting kernel
+# in one stream while another stream has to make progress (must be set before CUDA initialises)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

@@ -464,3 +464,50 @@ def test_small_batches_replay_a_cuda_graph_bit_identically(nb, world):
             np.testing.assert_array_equal(r["scores"].view(np.uint32), runs[0]["scores"].view(np.uint32))
     finally:
         world["scorer"].set_precision(nb.SCORER_EXACT)
+
+
+@pytest.mark.parametrize("precision", ["exact", "tensor"])
+def test_distributed_scoring_is_bit_identical_to_the_unsharded_search(nb, world, precision):
+    """nann_search_distributed: two members in one process (one device, one stream each): the graph is replicated, the
+    embedding table row-sharded, each member traverses ITS queries and scores the candidates it owns for both.  Ids and
+    scores must equal nann_search_batch on the unsharded index bit for bit, in both scorer precisions, over several
+    calls (window reuse) and with a failing query in the batch."""
+    import torch
+    from nann_b200.distributed import DistGroup
+    T = world["T"]
+    n = world["emb"].shape[0]
+    B, n_seq, G = 6, 3, 2
+    sc = nb.Scorer.mlp(*world["mlp"])
+    if precision == "tensor":
+        sc.set_precision(nb.SCORER_TENSOR)
+    ref = nb.Searcher(world["ix"], sc, G * B, T)
+    per = -(-n // G)
+    members, searchers, keep = [], [], []
+    for r in range(G):
+        lo, hi = r * per, min((r + 1) * per, n)
+        ix = nb.Index.from_arrays_sharded(n, world["emb"][lo:hi], lo, world["item_ids"], world["ep"], world["values"], world["row_splits"])
+        se = nb.Searcher(ix, sc, B, T)
+        with pytest.raises(nb.NannError):              # a slice of the table cannot be searched on its own
+            se.search(world["queries"][:B], T)
+        keep.append(ix); searchers.append(se)
+        members.append(DistGroup(se, r, G))
+    DistGroup.connect_local(members)
+    streams = [torch.cuda.Stream() for _ in range(G)]
+    outs = [[(torch.empty((B, T[5]), dtype=torch.int64, device="cuda"), torch.empty((B, T[5]), dtype=torch.float32, device="cuda"),
+              torch.empty((B,), dtype=torch.int32, device="cuda")) for _ in range(n_seq)] for _ in range(G)]
+    users = torch.from_numpy(world["queries"][:n_seq * G * B]).cuda()
+    torch.cuda.synchronize()
+    for i in range(n_seq):
+        for r in range(G):                             # rank r owns queries [r*B, (r+1)*B) of the global batch i
+            u = users[(i * G + r) * B:(i * G + r + 1) * B]
+            members[r].search(u, T, *outs[r][i], stream=streams[r])
+    torch.cuda.synchronize()
+    for m in members:
+        m.check()
+    for i in range(n_seq):
+        want = ref.search(world["queries"][i * G * B:(i + 1) * G * B], T)
+        assert np.all(want["status"] == 0)
+        for r in range(G):
+            np.testing.assert_array_equal(outs[r][i][0].cpu().numpy(), want["ids"][r * B:(r + 1) * B])
+            np.testing.assert_array_equal(outs[r][i][1].cpu().numpy().view(np.uint32), want["scores"][r * B:(r + 1) * B].view(np.uint32))
+            assert int(outs[r][i][2].sum()) == 0
