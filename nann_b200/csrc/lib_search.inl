@@ -868,15 +868,26 @@ static nann_status search_deliver(nann_searcher* s, int B, int k, int64_t* out_i
   const int64_t mb = s->max_batch;
   const bool dev_ids = !out_item_ids || is_device_ptr(out_item_ids), dev_sc = !out_scores || is_device_ptr(out_scores);
   const bool dev_st = !out_status || is_device_ptr(out_status);
+  // device outputs are written by a KERNEL: a device-to-device cudaMemcpyAsync is an implicit synchronisation point
+  // between streams ("a memory copy between two addresses to the same device memory", CUDA programming guide), which
+  // deadlocks two group members driven from one process: the copy of member 0 waits behind its flag-waiting kernel and
+  // member 1's kernels, issued after the copy, wait behind the copy
+  auto copy_words = [&](void* dst, const void* src, int64_t n_words) -> nann_status {
+    NANN_LAUNCH(copy_floats_kernel, (unsigned)std::min<int64_t>(ceil_div(n_words, 256), 148 * 4), 256, 0, st, (const float*)src,
+                (float*)dst, n_words);
+    return NANN_OK;
+  };
   if (k > 0) {
-    if (out_item_ids)
-      NANN_CUDA(cudaMemcpyAsync(out_item_ids, s->out_item, (size_t)B * k * 8,
-                                dev_ids ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
-    if (out_scores)
-      NANN_CUDA(cudaMemcpyAsync(out_scores, s->out_sc, (size_t)B * k * 4,
-                                dev_sc ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+    if (out_item_ids) {
+      if (dev_ids) NANN_TRY(copy_words(out_item_ids, s->out_item, (int64_t)B * k * 2));
+      else NANN_CUDA(cudaMemcpyAsync(out_item_ids, s->out_item, (size_t)B * k * 8, cudaMemcpyDeviceToHost, st));
+    }
+    if (out_scores) {
+      if (dev_sc) NANN_TRY(copy_words(out_scores, s->out_sc, (int64_t)B * k));
+      else NANN_CUDA(cudaMemcpyAsync(out_scores, s->out_sc, (size_t)B * k * 4, cudaMemcpyDeviceToHost, st));
+    }
   }
-  if (out_status && dev_st) NANN_CUDA(cudaMemcpyAsync(out_status, s->status, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
+  if (out_status && dev_st) NANN_TRY(copy_words(out_status, s->status, B));
   if (dev_ids && dev_sc && dev_st && !stats && !s->profile) return NANN_OK;
 
   s->h_round_n.resize((size_t)5 * mb); s->h_round_exp.resize((size_t)5 * mb); s->h_status.resize(B);

@@ -471,7 +471,7 @@ def test_distributed_scoring_is_bit_identical_to_the_unsharded_search(nb, world,
     """nann_search_distributed: two members in one process (one device, one stream each): the graph is replicated, the
     embedding table row-sharded, each member traverses ITS queries and scores the candidates it owns for both.  Ids and
     scores must equal nann_search_batch on the unsharded index bit for bit, in both scorer precisions, over several
-    calls (window reuse) and with a failing query in the batch."""
+    calls (window reuse)."""
     import torch
     from nann_b200.distributed import DistGroup
     T = world["T"]
