@@ -747,6 +747,164 @@ def run_b200(args, T, rank, world, local_rank):
     return out
 
 
+def run_b200_dist(args, T, rank, world, local_rank):
+    """N > 1, --mode dist: ONE graph (replicated), the embedding table row-sharded, the global batch partitioned; every
+    scoring round the candidates travel to the ranks that own their rows and the scores come back (nann_search_distributed).
+    Results are bit-identical to the one-GPU search, so recall IS the one-GPU operating point."""
+    import torch
+    import torch.distributed as dist
+    import nann_b200 as nb
+    from nann_b200 import scorer_weights as sw
+    from nann_b200.distributed import DistGroup
+    torch.cuda.set_device(local_rank)
+    dev = f"cuda:{local_rank}"
+    k, b = T[5], args.batch
+    B = b * world
+    if rank == 0:
+        get_shard(args.n_items, 1, 0, dev)                   # one graph over the whole corpus, built once, read by everybody
+    dist.barrier()
+    full = get_shard(args.n_items, 1, 0, dev)
+    n = full["emb"].shape[0]
+    per = -(-n // world)
+    lo, hi = rank * per, min((rank + 1) * per, n)
+    ix = nb.Index.from_arrays_sharded(n, full["emb"][lo:hi], lo, full["item_ids"], full["ep"], full["values"], full["row_splits"], device=local_rank)
+    sc = nb.Scorer.mlp(*sw.mlp_weights(seed=3), device=local_rank)
+    if args.precision == "tensor":
+        sc.set_precision(nb.SCORER_TENSOR)
+    se = nb.Searcher(ix, sc, b, T)
+    grp = DistGroup(se, rank, world)
+    grp.connect_torch()
+    n_steps = args.warmup + args.steps
+    queries = nix().synthetic_queries(full["emb"], B * n_steps, seed=2)      # the same global batches on every rank
+    n_eval = max(world, args.eval_queries // world * world)
+    eval_q = nix().synthetic_queries(full["emb"], n_eval, seed=5)
+    stream = torch.cuda.Stream(device=dev)
+    mine = lambda i: slice(i * B + rank * b, i * B + (rank + 1) * b)          # noqa: E731  this rank's queries of global batch i
+    q_dev = torch.from_numpy(queries).to(dev)
+    q_pin = torch.from_numpy(queries).pin_memory()
+    outs = [(torch.empty((b, k), dtype=torch.int64, device=dev), torch.empty((b, k), dtype=torch.float32, device=dev),
+             torch.empty((b,), dtype=torch.int32, device=dev)) for _ in range(2)]
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device(i):
+        grp.search(q_dev[mine(i)], T, *outs[i & 1], stream=stream)
+
+    def step_profile(i):
+        grp.search(q_dev[mine(i)], T, *outs[i & 1], stream=stream, want_stats=True)
+
+    def step_e2e(i):
+        return grp.search(q_pin[mine(i)].numpy(), T)
+
+    step_wall = []
+
+    def timed(fn, profile):
+        for w in range(args.warmup):
+            fn(w)
+        barrier()
+        se.set_profile(profile)
+        l0 = nb.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        del step_wall[:]
+        t0 = time.perf_counter()
+        timed.window = [t0, t0]
+        e0.record(stream)
+        for s_ in range(args.steps):
+            ts = time.perf_counter()
+            fn(args.warmup + s_)
+            step_wall.append(time.perf_counter() - ts)
+        e1.record(stream)
+        barrier()
+        wall = time.perf_counter() - t0
+        timed.window[1] = t0 + wall
+        dev_ms = e0.elapsed_time(e1)
+        prof = se.profile() if profile else None
+        se.set_profile(False)
+        t = torch.tensor([dev_ms, wall * 1000.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t[0].item(), t[1].item(), nb.launch_count() - l0, prof
+
+    with ClockSampler(local_rank) as clk:
+        dev_ms, _, launches, _ = timed(step_device, False)
+        clk.window(*timed.window)
+    grp.check()
+    prof_ms, _, _, prof = timed(step_profile, True)
+    e2e_dev_ms, e2e_wall_ms, _, _ = timed(step_e2e, False)
+    lat = sorted(step_wall)
+    latency_ms = {"p50": 1000.0 * lat[len(lat) // 2], "max": 1000.0 * lat[-1], "batch": B,
+                  "what": "wall time of one public API call per rank (host queries in, host ids+scores out), all ranks in step"}
+
+    # ---- outside the timed region: recall vs brute force, and identity with the one-GPU search
+    extra = {}
+    try:
+        be = n_eval // world
+        _, ids_e, st_e = grp.search(eval_q[rank * be:(rank + 1) * be], T)
+        g_ids = [torch.empty((be, k), dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(g_ids, torch.from_numpy(ids_e).to(dev))
+        got = torch.cat(g_ids, 0).cpu().numpy()
+        emb_dev = torch.from_numpy(full["emb"][lo:hi]).to(dev)
+        truth = Truth(nb, sc, emb_dev, torch.from_numpy(full["item_ids"][lo:hi]).to(dev), eval_q, k, world, dev)
+        del emb_dev
+        extra["recall_at_k_vs_bruteforce"] = truth.recall(got)
+        extra["recall_queries"] = n_eval
+        if rank == 0:
+            ix1 = nb.Index.from_arrays(full["emb"], full["item_ids"], full["ep"], full["values"], full["row_splits"], device=local_rank)
+            one = nb.Searcher(ix1, sc, n_eval, T).search(eval_q, T)
+            extra["recall_target"] = truth.recall(one["ids"])
+            extra["recall_target_source"] = "the unsharded index searched on rank 0, same queries, this run"
+            extra["ids_bit_identical_to_one_gpu_search"] = bool(np.array_equal(one["ids"], got))
+            extra["recall_held"] = bool(extra["recall_at_k_vs_bruteforce"] >= extra["recall_target"] - RECALL_TOL)
+            extra["one_gpu_rows_scored_per_query"] = float(one["n_scored"].sum()) / n_eval
+            del ix1
+    except Exception as e:
+        extra["recall_error"] = repr(e)[:200]
+    barrier()
+    grp.close()
+    if rank != 0:
+        return None
+    pk = peaks()
+    rows = prof["rows_scored"]
+    score_ms = prof["ms"]["score"]
+    n_score = max(prof["launches"]["score"], 1)
+    ach_tf = rows * 2.0 * MAC_PER_ROW / (score_ms / 1000.0) / 1e12 if score_ms > 0 else 0.0
+    cfg = workload_config(args, T, 1)
+    cfg["workload"] = cfg["workload"].replace(f"batch={args.batch} queries", f"global batch={B} queries ({args.batch} per GPU)") + f", {world} GPUs"
+    cfg["parallelism"] = (f"distributed scoring x{world}: ONE graph (replicated with the enter points and item ids), the embedding table "
+                          f"row-sharded ({per} rows per GPU), the global batch partitioned; per scoring round the candidates go to the ranks "
+                          f"that own their rows and the scores come back (stores into IPC-mapped peer windows over NVLink); weak scaling")
+    out = {
+        "metric": "queries/sec at fixed recall@200", "value": B * args.steps / (dev_ms / 1000.0), "unit": "queries/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": dict(cfg, scorer_precision=args.precision, mode="dist"),
+        "exchange": "in-library (csrc/lib_dist.inl): bucket / return kernels store candidate ids and scores into the owners' / sources' windows, "
+                    "one-warp flag waits on the same stream; 11 flag round trips per step",
+        "e2e": {"value": B * args.steps / (e2e_wall_ms / 1000.0), "unit": "queries/s", "h2d_bytes_per_step": B * 128 * 4,
+                "d2h_bytes_per_step": B * k * 12 + B * 4,
+                "timing": "wall clock around the public API call with pinned host inputs and host outputs (every rank its slice)",
+                "device_ms_per_step": e2e_dev_ms / args.steps},
+        "latency_ms": latency_ms, "gpu_launches": launches, "clocks": clk.summary(),
+        "roofline": {
+            "kernel": "mlp_tc8_kernel (fused row gather + 2x512 MLP, tcgen05 fp16 hi/lo split, cluster-pair neuron split)" if args.precision == "tensor"
+                      else "mlp_exact_kernel (fused row gather + 2x512 MLP, fp32 FFMA)",
+            "bound": "tensor", "achieved": ach_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach_tf / pk["tf_sustained"],
+            "peak_source": f"bf16 dense sustained, of {pk['source']}", "traffic": _ncu_traffic(args.precision),
+            "algorithmic_flops_per_row": 2 * MAC_PER_ROW, "rows_per_launch": rows / n_score, "avg_launch_ms": score_ms / n_score,
+            "note": "in this mode the CUDA events bracket a whole distributed scoring round (bucket + flag wait + scorer kernel + return + "
+                    "flag wait + unbucket), so `achieved` understates the scorer kernel by the exchange time; rows = rows of this rank's "
+                    "queries (each rank scores as many rows of other ranks' queries as others score of its own)"},
+        "roofline_gather": _gather_roofline(),
+        "stages_ms_per_step": {k2: v / args.steps for k2, v in prof["ms"].items()},
+        "profile_pass_ms_per_step": prof_ms / args.steps,
+        "rows_scored_per_query": rows / (b * args.steps),
+        "cpu_baseline": None,
+    }
+    out.update(extra)
+    return out
+
+
 def _ncu_traffic(precision):
     """DRAM bytes of one launch of the dominant kernel, from the committed `ncu --set full` capture (profiles/)."""
     try:
@@ -780,6 +938,9 @@ def main():
     ap.add_argument("--shard-scales", default="", help="N>1: five comma-separated per-beam scales (e.g. the ones a smaller corpus calibrated to)")
     ap.add_argument("--cpu-shard-sample", type=int, default=0,
                     help="N>1: rank 0 also times the CPU port on ITS shard with the per-shard beams for this many queries")
+    ap.add_argument("--mode", default=os.environ.get("NANN_BENCH_MODE", "shard"), choices=["shard", "dist"],
+                    help="N>1: shard = own HNSW per GPU + one exchange of per-shard top-k (calibrated beams); dist = one graph, "
+                         "embedding table row-sharded, distributed scoring (bit-identical to the one-GPU search)")
     ap.add_argument("--no-replica", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -819,7 +980,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     try:
-        out = run_b200(args, T, rank, world, local_rank)
+        out = run_b200_dist(args, T, rank, world, local_rank) if (world > 1 and args.mode == "dist") else run_b200(args, T, rank, world, local_rank)
         if out is not None:
             emit(out)
     finally:
