@@ -224,6 +224,9 @@ nann_status nann_dist_group_create(const nann_searcher_t* s, int rank, int world
              cudaMemset(g->error, 0, sizeof(int)) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
     rc = fail(NANN_INTERNAL, "distributed-scoring group setup failed: %s", cudaGetErrorString(cudaGetLastError()));
   }
+  // the tensor-core scorer's tile list for the G*B pseudo-queries, sized now: growing it inside a call would put a
+  // cudaMalloc / cudaFree (device-wide synchronisation) between the enqueues of two members driven by one thread
+  if (rc == NANN_OK) rc = nann::tc_ws_ensure(&g->svc_ws, (int)rows, (int64_t)rows * ceil_div(g->cap, nann::TC_M));
   if (rc != NANN_OK) { nann_dist_group_destroy(g); return rc; }
   g->peer[rank] = g->window;
   if (world == 1) g->connected = true;

@@ -700,8 +700,14 @@ static nann_status search_core(nann_searcher* s, int B, const int32_t T[6], cuda
     const int64_t smem = cap * 4 + tsize * 2;
     t_begin(1);
     if (!force_warp && f_n > 0 && f_n <= EFC_MAX_FRONTIER && cap > 0 && cap < 65535 && smem <= 200 * 1024) {
-      // per device, so set on every call (a process may hold searchers on several GPUs); it is a cheap driver call
-      NANN_CUDA(cudaFuncSetAttribute(expand_filter_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      // once per device (a process may hold searchers on several GPUs).  NOT on every call: the driver call can wait for
+      // launches of the function that are still pending, and a pending launch may sit behind a kernel that waits for work
+      // this host thread has yet to enqueue (two group members driven from one thread)
+      static std::atomic<bool> efc_attr[64];
+      if (!efc_attr[ix->device & 63].load(std::memory_order_acquire)) {
+        NANN_CUDA(cudaFuncSetAttribute(expand_filter_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        efc_attr[ix->device & 63].store(true, std::memory_order_release);
+      }
       NANN_LAUNCH(expand_filter_cta_kernel, (unsigned)B, EFC_THREADS, (size_t)smem, st,
                   ix->nbr_values[level], ix->nbr_rs[level], frontier, f_stride, f_n, s->bitmap, s->n_words,
                   s->cand_ids, s->maxc, s->round_n + r * mb, s->round_exp + r * mb, s->status, (int)cap, (int)tsize);
