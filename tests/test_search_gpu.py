@@ -467,11 +467,44 @@ def test_small_batches_replay_a_cuda_graph_bit_identically(nb, world):
 
 
 @pytest.mark.parametrize("precision", ["exact", "tensor"])
-def test_distributed_scoring_is_bit_identical_to_the_unsharded_search(nb, world, precision):
-    """nann_search_distributed: two members in one process (one device, one stream each): the graph is replicated, the
-    embedding table row-sharded, each member traverses ITS queries and scores the candidates it owns for both.  Ids and
-    scores must equal nann_search_batch on the unsharded index bit for bit, in both scorer precisions, over several
-    calls (window reuse)."""
+def test_distributed_scoring_world1_is_bit_identical_to_the_plain_search(nb, world, precision):
+    """nann_search_distributed with a group of ONE: every candidate is owned by this rank, but the whole exchange path
+    runs (bucket -> own request window -> scorer on the pseudo-queries -> return -> unbucket, flags and one-warp waits).
+    Ids and scores must equal nann_search_batch bit for bit, over several calls and batch sizes."""
+    import torch
+    from nann_b200.distributed import DistGroup
+    T = world["T"]
+    n = world["emb"].shape[0]
+    sc = nb.Scorer.mlp(*world["mlp"])
+    if precision == "tensor":
+        sc.set_precision(nb.SCORER_TENSOR)
+    ref = nb.Searcher(world["ix"], sc, 16, T)
+    ix = nb.Index.from_arrays_sharded(n, world["emb"], 0, world["item_ids"], world["ep"], world["values"], world["row_splits"])
+    se = nb.Searcher(ix, sc, 16, T)
+    grp = DistGroup(se, 0, 1)
+    side = torch.cuda.Stream()
+    for B in (16, 5, 16):
+        users = world["queries"][:B]
+        sc_h, id_h, st_h = grp.search(users, T)                       # host outputs
+        want = ref.search(users, T)
+        np.testing.assert_array_equal(id_h, want["ids"])
+        np.testing.assert_array_equal(sc_h.view(np.uint32), want["scores"].view(np.uint32))
+        assert np.all(st_h == 0)
+        o = (torch.empty((B, T[5]), dtype=torch.int64, device="cuda"), torch.empty((B, T[5]), dtype=torch.float32, device="cuda"),
+             torch.empty((B,), dtype=torch.int32, device="cuda"))
+        grp.search(torch.from_numpy(users).cuda(), T, *o, stream=side)   # device outputs, enqueue only
+        torch.cuda.synchronize()
+        grp.check()
+        np.testing.assert_array_equal(o[0].cpu().numpy(), want["ids"])
+        np.testing.assert_array_equal(o[1].cpu().numpy().view(np.uint32), want["scores"].view(np.uint32))
+
+
+@pytest.mark.parametrize("precision", ["exact", "tensor"])
+def test_distributed_scoring_two_members_two_threads(nb, world, precision):
+    """Two members on ONE device, each driven by its own host thread and stream (the arrangement of a server with one
+    thread per GPU): the graph is replicated, the embedding table row-sharded, each member traverses ITS queries and scores
+    the candidates it owns for both.  Ids and scores equal nann_search_batch on the unsharded index bit for bit."""
+    import threading
     import torch
     from nann_b200.distributed import DistGroup
     T = world["T"]
@@ -482,32 +515,36 @@ def test_distributed_scoring_is_bit_identical_to_the_unsharded_search(nb, world,
         sc.set_precision(nb.SCORER_TENSOR)
     ref = nb.Searcher(world["ix"], sc, G * B, T)
     per = -(-n // G)
-    members, searchers, keep = [], [], []
+    members, keep = [], []
     for r in range(G):
         lo, hi = r * per, min((r + 1) * per, n)
         ix = nb.Index.from_arrays_sharded(n, world["emb"][lo:hi], lo, world["item_ids"], world["ep"], world["values"], world["row_splits"])
         se = nb.Searcher(ix, sc, B, T)
         with pytest.raises(nb.NannError):              # a slice of the table cannot be searched on its own
             se.search(world["queries"][:B], T)
-        keep.append(ix); searchers.append(se)
+        keep.append((ix, se))
         members.append(DistGroup(se, r, G))
     DistGroup.connect_local(members)
     streams = [torch.cuda.Stream() for _ in range(G)]
-    outs = [[(torch.empty((B, T[5]), dtype=torch.int64, device="cuda"), torch.empty((B, T[5]), dtype=torch.float32, device="cuda"),
-              torch.empty((B,), dtype=torch.int32, device="cuda")) for _ in range(n_seq)] for _ in range(G)]
-    users = torch.from_numpy(world["queries"][:n_seq * G * B]).cuda()
-    torch.cuda.synchronize()
-    for i in range(n_seq):
-        for r in range(G):                             # rank r owns queries [r*B, (r+1)*B) of the global batch i
-            u = users[(i * G + r) * B:(i * G + r + 1) * B]
-            members[r].search(u, T, *outs[r][i], stream=streams[r])
-    torch.cuda.synchronize()
-    for m in members:
-        m.check()
+    res = [[None] * n_seq for _ in range(G)]
+    errs = []
+
+    def drive(r):
+        try:
+            for i in range(n_seq):                     # rank r owns queries [r*B, (r+1)*B) of the global batch i
+                res[r][i] = members[r].search(world["queries"][(i * G + r) * B:(i * G + r + 1) * B], T, stream=streams[r])
+        except Exception as e:                         # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=drive, args=(r,)) for r in range(G)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
     for i in range(n_seq):
         want = ref.search(world["queries"][i * G * B:(i + 1) * G * B], T)
         assert np.all(want["status"] == 0)
         for r in range(G):
-            np.testing.assert_array_equal(outs[r][i][0].cpu().numpy(), want["ids"][r * B:(r + 1) * B])
-            np.testing.assert_array_equal(outs[r][i][1].cpu().numpy().view(np.uint32), want["scores"][r * B:(r + 1) * B].view(np.uint32))
-            assert int(outs[r][i][2].sum()) == 0
+            sc_h, id_h, st_h = res[r][i]
+            np.testing.assert_array_equal(id_h, want["ids"][r * B:(r + 1) * B])
+            np.testing.assert_array_equal(sc_h.view(np.uint32), want["scores"][r * B:(r + 1) * B].view(np.uint32))
+            assert np.all(st_h == 0)
