@@ -860,6 +860,23 @@ def run_b200_dist(args, T, rank, world, local_rank):
             del ix1
     except Exception as e:
         extra["recall_error"] = repr(e)[:200]
+    # ---- replica mode (what the reference's session pool does): the whole index on every GPU, no exchange
+    if not args.no_replica:
+        try:
+            ix1 = nb.Index.from_arrays(full["emb"], full["item_ids"], full["ep"], full["values"], full["row_splits"], device=local_rank)
+            se1 = nb.Searcher(ix1, sc, b, T)
+            o1 = [(torch.empty((b, k), dtype=torch.int64, device=dev), torch.empty((b, k), dtype=torch.float32, device=dev)) for _ in range(2)]
+
+            def step_replica(i):
+                se1.search_async(q_dev[mine(i)], T, *o1[i & 1], stream=stream)
+
+            r_ms, _, _, _ = timed(step_replica, False)
+            extra["replica_mode"] = {"value": B * args.steps / (r_ms / 1000.0), "unit": "queries/s", "ms_per_step": r_ms / args.steps,
+                                     "what": f"whole {n}-row index on every GPU, {b} queries per GPU and step, no exchange (the reference's "
+                                             f"replica model, blaze-benchmark/benchmark/core/model.cc:192-234); same results as the one-GPU search"}
+            del se1, ix1
+        except Exception as e:
+            extra["replica_mode"] = {"error": repr(e)[:200]}
     barrier()
     grp.close()
     if rank != 0:
@@ -938,7 +955,7 @@ def main():
     ap.add_argument("--shard-scales", default="", help="N>1: five comma-separated per-beam scales (e.g. the ones a smaller corpus calibrated to)")
     ap.add_argument("--cpu-shard-sample", type=int, default=0,
                     help="N>1: rank 0 also times the CPU port on ITS shard with the per-shard beams for this many queries")
-    ap.add_argument("--mode", default=os.environ.get("NANN_BENCH_MODE", "shard"), choices=["shard", "dist"],
+    ap.add_argument("--mode", default=os.environ.get("NANN_BENCH_MODE", "dist"), choices=["shard", "dist"],
                     help="N>1: shard = own HNSW per GPU + one exchange of per-shard top-k (calibrated beams); dist = one graph, "
                          "embedding table row-sharded, distributed scoring (bit-identical to the one-GPU search)")
     ap.add_argument("--no-replica", action="store_true")
@@ -980,7 +997,10 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     try:
-        out = run_b200_dist(args, T, rank, world, local_rank) if (world > 1 and args.mode == "dist") else run_b200(args, T, rank, world, local_rank)
+        # dist needs ONE graph over the whole corpus on every GPU: beyond 16M rows that build would have to be distributed
+        # too (not done), so those corpora use the per-shard-HNSW form
+        use_dist = world > 1 and args.mode == "dist" and args.n_items <= BIG
+        out = run_b200_dist(args, T, rank, world, local_rank) if use_dist else run_b200(args, T, rank, world, local_rank)
         if out is not None:
             emit(out)
     finally:

@@ -6,7 +6,7 @@ if [ "$N" = "2" ]; then
   timeout 600 python -m pytest tests/test_search_gpu.py -m gpu -x -q -k "distributed_scoring" 2>&1 | tail -5
   timeout 600 python -m pytest tests/test_dist_group_2gpu.py -m gpu -x -q 2>&1 | tail -3
 fi
-timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --mode dist --steps 10 --warmup 3 > gpurun_out/r2_bench_dist_n$N.json 2> gpurun_out/r2_bench_dist_n$N.err; echo "bench rc=$?"
+timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/r2_bench_dist_n$N.json 2> gpurun_out/r2_bench_dist_n$N.err; echo "bench rc=$?"
 grep "\[bench\]\|Error\|error" gpurun_out/r2_bench_dist_n$N.err | grep -v "rank [1-9]" | tail -8
 python - <<PY
 import json
