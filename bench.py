@@ -773,7 +773,16 @@ def run_b200_dist(args, T, rank, world, local_rank):
         sc.set_precision(nb.SCORER_TENSOR)
     se = nb.Searcher(ix, sc, b, T)
     grp = DistGroup(se, rank, world)
-    grp.connect_torch()
+    ok = torch.ones(1, device=dev)
+    try:
+        grp.connect_torch()
+    except Exception as e:                                   # no peer mappings in this container
+        log(f"[bench] rank {rank}: peer windows unavailable ({e!r})")
+        ok.zero_()
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if ok.item() == 0.0:                                     # every rank takes the same way out
+        grp.close()
+        return "fallback"
     n_steps = args.warmup + args.steps
     queries = nix().synthetic_queries(full["emb"], B * n_steps, seed=2)      # the same global batches on every rank
     n_eval = max(world, args.eval_queries // world * world)
@@ -1001,6 +1010,8 @@ def main():
         # too (not done), so those corpora use the per-shard-HNSW form
         use_dist = world > 1 and args.mode == "dist" and args.n_items <= BIG
         out = run_b200_dist(args, T, rank, world, local_rank) if use_dist else run_b200(args, T, rank, world, local_rank)
+        if isinstance(out, str):                             # peer windows could not be mapped: per-shard HNSW + torch transport
+            out = run_b200(args, T, rank, world, local_rank)
         if out is not None:
             emit(out)
     finally:
