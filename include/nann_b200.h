@@ -14,7 +14,13 @@
  *                                 UO/blaze_op/blaze_xla_kernel.cc:24-33,194-258, blaze_xla_predictor.cc:360-459
  *   nann_index_*, nann_search_*   the whole exec.pb dataflow, build_opt_graph.py:69-160, for a
  *                                 BATCH of queries in one call (the reference runs batch=1)
- *   nann_merge_topk               new: per-shard top-k merge after the NCCL allgather
+ *   nann_merge_topk               new: per-shard top-k merge after an all-gather (torch.distributed transport)
+ *   nann_shard_group_*, nann_search_sharded   new: sharded HNSW, exchange + merge inside the library over NVLink peer windows
+ *   nann_dist_group_*, nann_search_distributed, nann_index_create_sharded
+ *                                 new: one graph, embedding table row-sharded, distributed scoring (bit-identical results)
+ *   nann_bloom_filter_difference_*  BloomFilterDifference<T>  UO/bitmap_op/bitmap_ops.cc:264-432
+ *   nann_scorer_set_admission     BlazeXlaOp::Schedule    UO/blaze_op/blaze_xla_kernel.cc:87-101,221-258
+ *   nann_hnsw_build               faiss IndexHNSWFlat + CSR dump  NANN_impls/nann/delivery/build_hnsw_index.py:33-67
  *   nann_executor_*               blaze-benchmark's session pool + consumers
  *                                 blaze-benchmark/benchmark/core/model.cc:128-237, predict_request_consumer.cc:17-54
  *
@@ -45,7 +51,7 @@
 extern "C" {
 #endif
 
-#define NANN_B200_ABI_VERSION 1
+#define NANN_B200_ABI_VERSION 2
 
 typedef int nann_status;
 enum {

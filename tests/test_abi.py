@@ -33,7 +33,7 @@ def test_build_and_exports():
     assert len(names) >= 30
     missing = [n for n in names if not hasattr(lib, n)]
     assert not missing, missing
-    assert lib.nann_abi_version() == 1
+    assert lib.nann_abi_version() == 2
 
 
 def test_library_targets_sm_100a():
@@ -132,7 +132,7 @@ int main(void) {
   float in[4] = {1.f, 3.f, 2.f, 0.f}, val[2];
   int32_t idx[2];
   nann_status st;
-  if (nann_abi_version() != 1) return 2;
+  if (nann_abi_version() != NANN_B200_ABI_VERSION) return 2;
   st = nann_topk_v2_f32(in, 1, 4, 2, 1, val, idx, NULL);
   printf("%d %s\n", (int)st, st == NANN_OK ? "ok" : nann_last_error());
   if (st == NANN_OK) return (idx[0] == 1 && idx[1] == 2) ? 0 : 3;
