@@ -22,6 +22,7 @@ gets HTTP 400 with the op's message, as TF-Serving reports an InvalidArgument st
     python -m nann_b200.serve --embs-dir D/embeddings --index-dir D/index --port 8501
 """
 import argparse
+import os
 import queue
 import threading
 import time
@@ -30,7 +31,7 @@ import numpy as np
 
 
 class _Pending:
-    __slots__ = ("users", "topn", "event", "ids", "scores", "status", "error")
+    __slots__ = ("users", "topn", "event", "ids", "scores", "status", "error", "t0")
 
     def __init__(self, users, topn):
         self.users, self.topn = users, tuple(int(t) for t in topn)
@@ -38,12 +39,25 @@ class _Pending:
         self.ids = self.scores = self.status = self.error = None
 
 
+class Overloaded(RuntimeError):
+    """load shed the way BlazeXlaOp::Schedule sheds it (blaze_xla_kernel.cc:221-258)"""
+
+    def __init__(self, code, message):
+        super().__init__(message)
+        self.code = code           # 13 Internal ("waiting pool is full" / "blaze wait too long"), 4 DeadlineExceeded
+
+
 class DynamicBatcher:
     """backend(users f32[B, uf], level_topn) -> dict(ids i64[B,k], scores f32[B,k], status i32[B]);
-    requests are served in arrival order, one backend call per group of same-`level_topn` requests."""
+    requests are served in arrival order, one backend call per group of same-`level_topn` requests.
+    Admission control like the reference's BlazeXlaOp: with `wait_ms` == 0 a request is refused at once when `max_waiting`
+    requests are queued already (Internal "waiting pool is full", DENSE_MAX_WAITING_COUNT); with `wait_ms` > 0 a request
+    that has waited longer than that when its batch is formed is dropped (DeadlineExceeded "blaze wait too long")."""
 
-    def __init__(self, backend, max_batch_size=256, batch_timeout_us=200):
+    def __init__(self, backend, max_batch_size=256, batch_timeout_us=200, max_waiting=0, wait_ms=0):
         self.backend, self.max_batch = backend, int(max_batch_size)
+        self.max_waiting, self.wait_s = int(max_waiting), wait_ms * 1e-3
+        self.shed = 0
         self.timeout = batch_timeout_us * 1e-6
         self.q = queue.Queue()
         self.batches = []                      # sizes of the backend calls (observability / tests)
@@ -56,6 +70,10 @@ class DynamicBatcher:
         p = _Pending(np.ascontiguousarray(users, np.float32), topn)
         if p.users.shape[0] > self.max_batch:
             raise ValueError(f"request carries {p.users.shape[0]} users, max_batch_size is {self.max_batch}")
+        if self.wait_s == 0 and self.max_waiting > 0 and self.q.qsize() >= self.max_waiting:
+            self.shed += 1
+            raise Overloaded(13, f"waiting pool is full {self.q.qsize()}")
+        p.t0 = time.perf_counter()
         self.q.put(p)
         p.event.wait()
         if p.error is not None:
@@ -95,6 +113,18 @@ class DynamicBatcher:
                     break
                 group.append(p)
                 n += p.users.shape[0]
+            if self.wait_s > 0:                  # requests that waited too long are answered with DeadlineExceeded
+                now, live = time.perf_counter(), []
+                for g in group:
+                    if now - g.t0 > self.wait_s:
+                        g.error = Overloaded(4, f"blaze wait too long {int((now - g.t0) * 1e9)}")
+                        g.event.set()
+                        self.shed += 1
+                    else:
+                        live.append(g)
+                group, n = live, sum(g.users.shape[0] for g in live)
+                if not group:
+                    continue
             try:
                 res = self.backend(np.concatenate([g.users for g in group], 0), list(first.topn))
                 self.batches.append(n)
@@ -110,11 +140,11 @@ class DynamicBatcher:
                 g.event.set()
 
 
-def create_app(backend, user_floats, model_name="nann", max_batch_size=256, batch_timeout_us=200):
+def create_app(backend, user_floats, model_name="nann", max_batch_size=256, batch_timeout_us=200, max_waiting=0, wait_ms=0):
     from fastapi import FastAPI, HTTPException, Request
 
     app = FastAPI(title="nann-b200 serving")
-    batcher = DynamicBatcher(backend, max_batch_size, batch_timeout_us)
+    batcher = DynamicBatcher(backend, max_batch_size, batch_timeout_us, max_waiting, wait_ms)
     app.state.batcher = batcher
 
     @app.get("/v1/models/{name}")
@@ -145,6 +175,8 @@ def create_app(backend, user_floats, model_name="nann", max_batch_size=256, batc
         import anyio
         try:
             p = await anyio.to_thread.run_sync(batcher.submit, users, topn)
+        except Overloaded as e:                  # TF-Serving maps Internal -> 500, DeadlineExceeded -> 504
+            raise HTTPException(504 if e.code == 4 else 500, str(e))
         except Exception as e:                   # NannError / ValueError from the backend call
             raise HTTPException(400, str(e))
         if np.any(p.status != 0):
@@ -193,13 +225,13 @@ def encode_predict_response(model_name, signature, outputs):
 
 
 def create_grpc_server(backend, user_floats, address="[::]:8500", model_name="nann", max_batch_size=256,
-                       batch_timeout_us=200, max_workers=32):
+                       batch_timeout_us=200, max_workers=32, max_waiting=0, wait_ms=0):
     """grpc.Server answering /tensorflow.serving.PredictionService/Predict for inputs `comm_seq` (half or float
     [B, user_floats]) and `level_topn` (int32[6]) with output `top_k` (int64 [B, k]), through the same dynamic
     batcher as the REST front-end.  Returns (server, bound port, batcher); call server.start()."""
     from concurrent import futures
     import grpc
-    batcher = DynamicBatcher(backend, max_batch_size, batch_timeout_us)
+    batcher = DynamicBatcher(backend, max_batch_size, batch_timeout_us, max_waiting, wait_ms)
 
     def predict(request, context):
         try:
@@ -216,6 +248,8 @@ def create_grpc_server(backend, user_floats, address="[::]:8500", model_name="na
             if len(topn) != 6:
                 raise ValueError("level_topn must have 6 entries")
             p = batcher.submit(users, topn)
+        except Overloaded as e:
+            context.abort(grpc.StatusCode.DEADLINE_EXCEEDED if e.code == 4 else grpc.StatusCode.INTERNAL, str(e))
         except Exception as e:
             context.abort(grpc.StatusCode.INVALID_ARGUMENT, str(e))
         if np.any(p.status != 0):
@@ -272,6 +306,9 @@ def main():
     ap.add_argument("--max-level-topn", default="100,200,400,400,400,200")
     ap.add_argument("--max-batch-size", type=int, default=256)
     ap.add_argument("--batch-timeout-us", type=int, default=200)
+    ap.add_argument("--max-waiting", type=int, default=int(os.environ.get("DENSE_MAX_WAITING_COUNT", "0")),
+                    help="refuse requests when this many are queued (BlazeXlaOp's DENSE_MAX_WAITING_COUNT; 0 = never)")
+    ap.add_argument("--wait-ms", type=int, default=0, help="drop requests that waited longer (BlazeKernelOptions.wait_ms; 0 = never)")
     ap.add_argument("--scorer", default="attention", choices=["attention", "mlp"],
                     help="attention = the reference's model (Model.forward, 64-d item embeddings); mlp = the 2x512 bench scorer (128-d)")
     ap.add_argument("--scorer-weights", default=None,
@@ -299,9 +336,10 @@ def main():
 
     if args.grpc_port:
         server, _, _ = create_grpc_server(locked, sc.user_floats, f"{args.host}:{args.grpc_port}", max_batch_size=args.max_batch_size,
-                                          batch_timeout_us=args.batch_timeout_us)
+                                          batch_timeout_us=args.batch_timeout_us, max_waiting=args.max_waiting, wait_ms=args.wait_ms)
         server.start()
-    app = create_app(locked, sc.user_floats, max_batch_size=args.max_batch_size, batch_timeout_us=args.batch_timeout_us)
+    app = create_app(locked, sc.user_floats, max_batch_size=args.max_batch_size, batch_timeout_us=args.batch_timeout_us,
+                     max_waiting=args.max_waiting, wait_ms=args.wait_ms)
     uvicorn.run(app, host=args.host, port=args.port, log_level="warning")
 
 

@@ -47,3 +47,29 @@ def test_reference_arm_prints_exactly_one_json_line(tmp_path):
     assert d["impl"] == "reference" and d["unit"] == "queries/s" and d["higher_is_better"] is True
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["value"] > 0
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_blocked_corpus_is_sliceable_at_any_boundary(monkeypatch):
+    """corpora above bench.BIG are DEFINED block-wise: any [lo, hi) slice must equal the same rows of a larger slice"""
+    sys.path.insert(0, ROOT)
+    import bench
+    monkeypatch.setattr(bench, "BIG", 1000)
+    monkeypatch.setattr(bench, "N_BLOCKS", 8)
+    n = 4000                                             # 8 blocks of 500 rows
+    full_e, full_i = bench.corpus_rows(n, 0, n)
+    assert full_e.shape == (n, 128) and len(set(full_i.tolist())) == n
+    for lo, hi in ((0, 500), (250, 1250), (1999, 2001), (3500, 4000)):
+        e, i = bench.corpus_rows(n, lo, hi)
+        np.testing.assert_array_equal(e, full_e[lo:hi])
+        np.testing.assert_array_equal(i, full_i[lo:hi])
+    assert bench.query_pool(n).shape == (500, 128)
+
+
+def test_per_beam_shard_scales():
+    from nann_b200.distributed import shard_beams, shard_level_topn
+    T = [100, 200, 200, 200, 200, 200]
+    assert shard_beams(T, 1, [3, 3, 3, 3, 3]) == T
+    assert shard_beams(T, 8, [1.0] * 5) == shard_level_topn(T, 8)
+    t = shard_beams(T, 8, [1.0837, 1.275, 1.5, 1.5, 0.2953])
+    assert t == [14, 32, 38, 38, 8, 50]                  # the beams of the N = 8 and 100M runs (profiles/r02_bench_8gpu_sharded.json)
+    assert all(x >= 8 for x in t[:5]) and t[5] <= sum(t[1:5]) and 8 * t[5] >= T[5]

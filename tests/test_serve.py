@@ -150,3 +150,48 @@ def test_serving_cli_refuses_to_rank_with_random_weights():
         serve.load_scorer(_NB, sw, "attention", None, synthetic=False)
     assert serve.load_scorer(_NB, sw, "attention", None, synthetic=True) == ("attention", sw.ATT_BLOB)
     assert serve.load_scorer(_NB, sw, "mlp", None, synthetic=True) == ("mlp", 5)
+
+
+def test_batcher_sheds_load_like_blaze_xla_op():
+    """waiting pool full -> Internal at once (wait_ms == 0); waited too long -> DeadlineExceeded (wait_ms > 0)
+    (blaze_xla_kernel.cc:221-258)"""
+    import time
+    from nann_b200.serve import DynamicBatcher, Overloaded
+    gate = threading.Event()
+
+    def slow_backend(users, topn):
+        gate.wait(5)
+        k = topn[5]
+        return dict(ids=np.zeros((len(users), k), np.int64), scores=np.zeros((len(users), k), np.float32), status=np.zeros(len(users), np.int32))
+
+    b = DynamicBatcher(slow_backend, max_batch_size=1, batch_timeout_us=0, max_waiting=2, wait_ms=0)
+    res = []
+
+    def client():
+        try:
+            b.submit(np.zeros((1, 4), np.float32), [1, 1, 1, 1, 1, 1])
+            res.append("ok")
+        except Overloaded as e:
+            res.append((e.code, str(e)))
+
+    th = [threading.Thread(target=client) for _ in range(8)]
+    for t in th:
+        t.start()
+        time.sleep(0.02)                 # the first one is taken by the worker, two more queue up, the rest are refused
+    gate.set()
+    [t.join() for t in th]
+    assert res.count("ok") >= 3 and any(r != "ok" for r in res)
+    assert all(r == "ok" or (r[0] == 13 and "waiting pool is full" in r[1]) for r in res)
+    b.close()
+
+    gate.clear()
+    b = DynamicBatcher(slow_backend, max_batch_size=1, batch_timeout_us=0, wait_ms=30)
+    res.clear()
+    th = [threading.Thread(target=client) for _ in range(4)]
+    [t.start() for t in th]
+    time.sleep(0.2)                      # everybody behind the first request has now waited > 30 ms
+    gate.set()
+    [t.join() for t in th]
+    assert res.count("ok") >= 1 and any(r != "ok" for r in res)
+    assert all(r == "ok" or (r[0] == 4 and "blaze wait too long" in r[1]) for r in res)
+    b.close()
