@@ -19,34 +19,16 @@ L.nann_debug_tc_trace(C.c_void_p(buf.data_ptr()))
 nb.score_ids(sc, u, emb_d, ids)
 L.nann_debug_tc_trace(None)
 t = buf.cpu().numpy().reshape(64, 48)
-names = {0: "epi gather start", 1: "epi x_ready", 2: "mma d2_empty ok", 3: "mma x_ready ok", 4: "mma c0 issued", 5: "mma c1 issued",
-         6: "mma c2 issued", 7: "mma c3 issued", 8: "epi d1_full c0", 9: "epi d1_full c1", 10: "epi d1_full c2", 11: "epi d1_full c3",
-         12: "epi c0 done", 13: "epi c1 done", 14: "epi c2 done", 15: "epi c3 done", 16: "mma phase2 start", 25: "mma d2 committed",
-         26: "epi d2_full ok", 27: "epi tile done", 28: "prod h1_done c0", 29: "prod h1_done c1", 30: "prod h1_done c2", 31: "prod h1_done c3",
-         32: "prod tile start", 33: "prod tile issued"}
-names.update({42: "epi c1 tmem loaded", 43: "epi c1 stores issued", 44: "epi c1 fence done", 45: "epi2 math done"})
-for s in range(8):
-    names[17 + s] = f"mma a_full s{s}"; names[34 + s] = f"prod A s{s} issue"
-if os.environ.get("NANN_TC_KERNEL", "3") in ("5", "6"):
-    names = {0: "mma x_ready ok", 1: "mma pass0 issued", 2: "mma pass1 issued", 20: "B loop top", 21: "B epi2(0) done",
-             22: "B x_free ok", 23: "B gather done", 25: "B epi2(1) done"}
-    for h in range(2):
-        for c in range(8):
-            names[4 + h * 8 + c] = f"A slab h{h} c{c} written"; names[26 + h * 8 + c] = f"mma P2 h{h} c{c} issued"
-if os.environ.get("NANN_TC_KERNEL", "3") == "7":
-    names = {0: "epi iter start", 3: "mma iter start", 4: "mma L1c0 issued", 5: "mma L1c1 issued", 6: "mma pass0 issued", 7: "mma pass1 issued",
-             8: "epi epi1c0 done", 9: "epi epi2h0 done", 10: "epi epi1c1 done", 11: "epi gather(next) done", 12: "epi epi2h1+finish done"}
-if os.environ.get("NANN_TC_KERNEL", "3") == "8":
-    names = {0: "mma tile start", 1: "mma x units issued (d1_full committed)", 2: "mma d2_empty ok", 3: "mma unit 2 issued", 4: "mma unit 3 issued",
-             5: "mma unit 4 issued", 6: "mma unit 5 issued", 7: "mma d2 committed", 8: "epi iter start", 9: "epi d1_full ok", 10: "epi epi1 done",
-             11: "epi gather(next) loads issued", 12: "epi x(next) written", 13: "epi d2_full ok", 14: "epi tile done"}
+names = {0: "mma tile start", 1: "mma x units issued (d1_full committed)", 2: "mma d2_empty ok", 3: "mma unit 2 issued", 4: "mma unit 3 issued",
+         5: "mma unit 4 issued", 6: "mma unit 5 issued", 7: "mma d2 committed", 8: "epi iter start", 9: "epi d1_full ok", 10: "epi epi1 done",
+         11: "epi gather(next) loads issued", 12: "epi x(next) written", 13: "epi d2_full ok", 14: "epi tile done"}
 for tile in (10, 11):
     base = t[tile][0]
     print(f"--- tile {tile} (cycles from event 0)")
     for ev in sorted(names, key=lambda e: t[tile][e]):
         if t[tile][ev]: print(f"{t[tile][ev]-base:9d}  {names[ev]}")
 b11 = t[11][0]
-if os.environ.get("NANN_TC_KERNEL", "3") == "8":
+if True:
     print("tile 11 units: (a_full ok, hi stage ok, lo stage ok, all issued) from tile start")
     for u in range(10):
         print(f"   unit {u}:", [int(x - b11) for x in t.reshape(-1)[60 * 48 + 4 * u:60 * 48 + 4 * u + 4]])
