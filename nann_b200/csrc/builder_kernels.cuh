@@ -22,14 +22,16 @@ namespace nann {
 constexpr int KB_D = 128;           // embedding width the tensor-core pass is built for
 constexpr int KB_KC = 128;          // candidates kept per row between rounds
 constexpr int KB_CAP = 512;         // append buffer per row
-constexpr int KB_TN = 256;          // columns per tile (UMMA N)
-constexpr int KB_STRIP = 64;        // column tiles per work item (A tile re-read once per item: 2% of the B traffic)
+constexpr int KB_TN = 128;          // columns per tile (UMMA N)
+constexpr int KB_STRIP = 128;       // column tiles per work item (A tile re-read once per item: 1% of the B traffic)
+constexpr int KB_NB = 4;            // B-tile ring stages = accumulator buffers in TMEM (4 x 128 columns)
 constexpr int KB_QUEUE = 8;         // survivors a filter thread parks in shared memory before it reserves buffer slots
 constexpr int KB_THREADS = 320;     // warp 0 producer, warp 1 MMA, warps 2..9 filter epilogue
 constexpr int KB_A_BYTES = 32768;   // 128 rows x 128 k fp16
-constexpr int KB_B_BYTES = 65536;   // 256 rows x 128 k fp16
-constexpr int KB_HJ_SLOTS = 8;      // column-norm ring: the producer is at most 4 tiles ahead of the slowest epilogue thread
-constexpr int KB_SMEM_BYTES = 2 * KB_A_BYTES + 2 * KB_B_BYTES + KB_HJ_SLOTS * KB_TN * 4 + KB_QUEUE * 256 * 8 + 1024;
+constexpr int KB_B_BYTES = 32768;   // one B tile: 128 rows x 128 k fp16 (half an image block)
+constexpr int KB_BLK_BYTES = 65536; // image block: 256 rows x 128 k fp16
+constexpr int KB_HJ_SLOTS = 16;     // column-norm ring: the producer is at most 2 * KB_NB tiles ahead of the slowest epilogue thread
+constexpr int KB_SMEM_BYTES = 2 * KB_A_BYTES + KB_NB * KB_B_BYTES + KB_HJ_SLOTS * KB_TN * 4 + KB_QUEUE * 256 * 8 + 1024;
 constexpr int KB_MAX_CAND = 96;     // n_cand limit of the refine kernel (cap + M at level 0 with M = 32)
 
 // ---- exact row norms: sq[r] = sum_k x[k]^2, sequential fmaf chain in k (the oracle's definition)
@@ -74,7 +76,7 @@ __global__ void knn_image_kernel(const float* __restrict__ X, const float* __res
   }
   const int64_t blk = r >> 8;
   const int rr = (int)(r & 255), slab = c16 >> 3, chunk = c16 & 7;
-  *reinterpret_cast<uint4*>(img + blk * KB_B_BYTES + slab * 32768 + sw128_chunk_off(rr, chunk)) = out;
+  *reinterpret_cast<uint4*>(img + blk * KB_BLK_BYTES + slab * 32768 + sw128_chunk_off(rr, chunk)) = out;
   if (c16 == 0) hj[r] = r < s ? 0.5f * sq[r] : __int_as_float(0x7f800000);
 }
 
@@ -83,7 +85,7 @@ struct KnnArgs {
   float* tau; int* cnt; uint2* buf;      // per row of THIS launch's row range (index = row - row0)
   int64_t row0; int n_rb;                // first row (multiple of 128) and number of 128-row blocks of the range
   int64_t s;                             // members (rows >= s are padding)
-  int64_t col0; int n_ct;                // column chunk: first column (multiple of 256), number of 256-column tiles
+  int64_t col0; int n_ct;                // column chunk: first column (multiple of 256), number of 128-column tiles
   unsigned long long* overflow;          // appends dropped because a row's buffer was full
 };
 
@@ -111,18 +113,19 @@ knn_filter_kernel(KnnArgs p) {
   uint8_t* smem = kb_smem;
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* sA = smem;                         // 2 x 32 KB
-  uint8_t* sB = smem + 2 * KB_A_BYTES;        // 2 x 64 KB
-  float* hj_s = (float*)(sB + 2 * KB_B_BYTES);                  // [KB_HJ_SLOTS][256] sq_j / 2 of the tile's columns
+  uint8_t* sB = smem + 2 * KB_A_BYTES;        // KB_NB x 32 KB
+  float* hj_s = (float*)(sB + KB_NB * KB_B_BYTES);              // [KB_HJ_SLOTS][128] sq_j / 2 of the tile's columns
   uint2* queue = (uint2*)(hj_s + KB_HJ_SLOTS * KB_TN);          // [KB_QUEUE][256 filter threads] parked survivors
   uint64_t* bars = (uint64_t*)(queue + KB_QUEUE * 256);
-  uint32_t* tmem_slot = (uint32_t*)(bars + 16);
-  enum { A_FULL = 0, A_EMPTY = 2, B_FULL = 4, B_EMPTY = 6, D_FULL = 8, D_EMPTY = 10 };
+  uint32_t* tmem_slot = (uint32_t*)(bars + 24);
+  enum { A_FULL = 0, A_EMPTY = 2, B_FULL = 4, B_EMPTY = 4 + KB_NB, D_FULL = 4 + 2 * KB_NB, D_EMPTY = 4 + 3 * KB_NB };
+  static_assert(4 + 4 * KB_NB <= 24, "barrier block");
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(BAR(A_FULL + i), 1); mbar_init(BAR(A_EMPTY + i), 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(BAR(A_FULL + i), 1); mbar_init(BAR(A_EMPTY + i), 1); }
+    for (int i = 0; i < KB_NB; ++i) {
       mbar_init(BAR(B_FULL + i), 1); mbar_init(BAR(B_EMPTY + i), 1);
       mbar_init(BAR(D_FULL + i), 1); mbar_init(BAR(D_EMPTY + i), T2_EPI_THREADS);
     }
@@ -156,28 +159,29 @@ knn_filter_kernel(KnnArgs p) {
       mbar_wait(BAR(A_EMPTY + ab), ((ia >> 1) & 1) ^ 1);
       if (elect_one()) {
         const int64_t rb = (p.row0 >> 7) + rbi;                // global 128-row block
-        const uint8_t* src = p.img + (rb >> 1) * KB_B_BYTES + (rb & 1) * 16384;
+        const uint8_t* src = p.img + (rb >> 1) * KB_BLK_BYTES + (rb & 1) * 16384;
         mbar_expect_tx(BAR(A_FULL + ab), KB_A_BYTES);
         bulk_g2s(smem_u32(sA) + ab * KB_A_BYTES, src, 16384, BAR(A_FULL + ab));
         bulk_g2s(smem_u32(sA) + ab * KB_A_BYTES + 16384, src + 32768, 16384, BAR(A_FULL + ab));
       }
       for (int t = 0; t < nct; ++t, ++ib) {
-        const uint32_t st = ib & 1;
-        mbar_wait(BAR(B_EMPTY + st), ((ib >> 1) & 1) ^ 1);
+        const uint32_t st = ib % KB_NB;
+        mbar_wait(BAR(B_EMPTY + st), ((ib / KB_NB) & 1) ^ 1);
         if (elect_one()) {
-          const int64_t cb = (p.col0 >> 8) + ct0 + t;          // 256-row block of the image
-          // the column norms ride along (a global load per compare missed the few-KB L1 on every tile: 8.5k cycles per
-          // tile instead of ~1.2k).  Slot ib % 8 is free: B ring (2) + accumulator ring (2) keep this warp < 8 tiles ahead.
+          const int64_t ct = (p.col0 >> 7) + ct0 + t;          // 128-column tile = half of a 256-row image block
+          const uint8_t* src = p.img + (ct >> 1) * KB_BLK_BYTES + (ct & 1) * 16384;
+          // the column norms ride along (a global load per compare missed the few-KB L1 on every tile).  Slot ib % 16 is
+          // free: B ring (4) + accumulator ring (4) keep this warp fewer than 16 tiles ahead of the slowest filter thread.
           mbar_expect_tx(BAR(B_FULL + st), KB_B_BYTES + KB_TN * 4);
-          bulk_g2s(smem_u32(sB) + st * KB_B_BYTES, p.img + cb * KB_B_BYTES, 32768, BAR(B_FULL + st));
-          bulk_g2s(smem_u32(sB) + st * KB_B_BYTES + 32768, p.img + cb * KB_B_BYTES + 32768, 32768, BAR(B_FULL + st));
-          bulk_g2s(smem_u32(hj_s) + (ib % KB_HJ_SLOTS) * KB_TN * 4, p.hj + cb * KB_TN, KB_TN * 4, BAR(B_FULL + st));
+          bulk_g2s(smem_u32(sB) + st * KB_B_BYTES, src, 16384, BAR(B_FULL + st));
+          bulk_g2s(smem_u32(sB) + st * KB_B_BYTES + 16384, src + 32768, 16384, BAR(B_FULL + st));
+          bulk_g2s(smem_u32(hj_s) + (ib % KB_HJ_SLOTS) * KB_TN * 4, p.hj + ct * KB_TN, KB_TN * 4, BAR(B_FULL + st));
         }
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer: D[buf] = A (128 x 128) . B^T (256 x 128), 8 x (M128 N256 K16) =================
-    const uint32_t idesc = umma_idesc_f16(128, 256);
+    // ================= MMA issuer: D[buf] = A (128 x 128) . B^T (128 x 128), 8 x (M128 N128 K16) =================
+    const uint32_t idesc = umma_idesc_f16(128, 128);
     uint32_t ia = 0, ib = 0;
     for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x, ++ia) {
       int rbi, ct0, nct;
@@ -186,18 +190,18 @@ knn_filter_kernel(KnnArgs p) {
       mbar_wait(BAR(A_FULL + ab), (ia >> 1) & 1);
       const uint64_t dA = umma_desc_sw128(smem_u32(sA) + ab * KB_A_BYTES);
       for (int t = 0; t < nct; ++t, ++ib) {
-        const uint32_t st = ib & 1;
-        mbar_wait(BAR(B_FULL + st), (ib >> 1) & 1);
-        mbar_wait(BAR(D_EMPTY + st), ((ib >> 1) & 1) ^ 1);     // accumulator buffer == B stage parity
+        const uint32_t st = ib % KB_NB;
+        mbar_wait(BAR(B_FULL + st), (ib / KB_NB) & 1);
+        mbar_wait(BAR(D_EMPTY + st), ((ib / KB_NB) & 1) ^ 1);  // accumulator buffer index == B stage index
         tc_fence_after();
         if (elect_one()) {
           const uint64_t dB = umma_desc_sw128(smem_u32(sB) + st * KB_B_BYTES);
-          const uint32_t d = tmem + st * 256;
+          const uint32_t d = tmem + st * 128;
 #pragma unroll
           for (int slab = 0; slab < 2; ++slab)
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
-              tc_mma_f16(d, dA + (uint64_t)((slab * 16384 + ks * 32) >> 4), dB + (uint64_t)((slab * 32768 + ks * 32) >> 4), idesc,
+              tc_mma_f16(d, dA + (uint64_t)((slab * 16384 + ks * 32) >> 4), dB + (uint64_t)((slab * 16384 + ks * 32) >> 4), idesc,
                          (slab | ks) ? 1u : 0u);
           tc_commit(BAR(B_EMPTY + st));
           tc_commit(BAR(D_FULL + st));
@@ -230,19 +234,19 @@ knn_filter_kernel(KnnArgs p) {
       float hi = __int_as_float(0x7f800000), sqi = 0.f;                  // pad rows: nothing passes
       if (row < p.s) { sqi = p.sq[row]; hi = 0.5f * (sqi - p.tau[lrow]); }
       for (int t = 0; t < nct; ++t, ++ib) {
-        const uint32_t st = ib & 1;
-        mbar_wait(BAR(D_FULL + st), (ib >> 1) & 1);
+        const uint32_t st = ib % KB_NB;
+        mbar_wait(BAR(D_FULL + st), (ib / KB_NB) & 1);
         tc_fence_after();
-        const int64_t c_tile = p.col0 + (int64_t)(ct0 + t) * KB_TN + col_half * 128;
-        const float* hj_t = hj_s + (ib % KB_HJ_SLOTS) * KB_TN + col_half * 128;
-        const uint32_t tb = tmem + t_lane + st * 256 + (uint32_t)(col_half * 128);
+        const int64_t c_tile = p.col0 + (int64_t)(ct0 + t) * KB_TN + col_half * 64;
+        const float* hj_t = hj_s + (ib % KB_HJ_SLOTS) * KB_TN + col_half * 64;
+        const uint32_t tb = tmem + t_lane + st * 128 + (uint32_t)(col_half * 64);
         // One test per 32 columns instead of one per 4: t = max_c (dot_c - sq_c / 2) > h_i ?  (survivors are rare: ~128 per
         // row and round).  The next 32 columns are already on their way from TMEM while these are reduced, and the
         // accumulator is handed back to the MMA warp as soon as the last TMEM read has landed, not after the math.
         uint32_t va[32], vb[32];
         auto chunk = [&](uint32_t (&v)[32], uint32_t (&vnext)[32], int ch) {
           tc_ld_wait_dep(v);
-          if (ch < 3) tc_ld32_nowait(tb + (ch + 1) * 32, vnext);
+          if (ch < 1) tc_ld32_nowait(tb + (ch + 1) * 32, vnext);
           else { tc_fence_before(); mbar_arrive(BAR(D_EMPTY + st)); }
           float4 h[8];
 #pragma unroll
@@ -274,8 +278,6 @@ knn_filter_kernel(KnnArgs p) {
         tc_ld32_nowait(tb, va);
         chunk(va, vb, 0);
         chunk(vb, va, 1);
-        chunk(va, vb, 2);
-        chunk(vb, va, 3);
       }
       flush(lrow);
     }

@@ -64,7 +64,7 @@ static nann_status build_level(const float* emb_d, int64_t n, const std::vector<
   const bool all_pairs = s - 1 <= KB_KC;
   DevMem img, hj;
   if (!all_pairs) {
-    NANN_TRY(img.alloc((size_t)s_pad / 256 * KB_B_BYTES));
+    NANN_TRY(img.alloc((size_t)s_pad / 256 * KB_BLK_BYTES));
     NANN_TRY(hj.alloc((size_t)s_pad * 4));
     NANN_LAUNCH(knn_image_kernel, (unsigned)ceil_div(s_pad * 16, 256), 256, 0, st, X, sq.as<float>(), s, s_pad, img.as<uint8_t>(), hj.as<float>());
     NANN_CUDA(cudaFuncSetAttribute(knn_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KB_SMEM_BYTES));
