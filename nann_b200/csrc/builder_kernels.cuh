@@ -233,69 +233,51 @@ knn_filter_kernel(KnnArgs p) {
       const int64_t row = p.row0 + lrow;
       float hi = __int_as_float(0x7f800000), sqi = 0.f;                  // pad rows: nothing passes
       if (row < p.s) { sqi = p.sq[row]; hi = 0.5f * (sqi - p.tau[lrow]); }
-      // One test per 32 columns: max_c (dot_c - sq_c / 2) > h_i ?  (survivors are rare: ~128 per row and round), element by
-      // element only where it fires.  Each filter warp touches EVERY tile, so what bounds the kernel is the latency of one
-      // warp's TMEM reads (tcgen05.ld + wait, ~1.5k cycles per 128-column tile when done tile after tile against 512 cycles
-      // of MMA): the reads of tile t+1 are issued BEFORE the math of tile t (two register sets, loop unrolled by two), and
-      // the accumulator goes back to the MMA warp as soon as its reads have landed, not after the math.
-      auto issue = [&](uint32_t (&v0)[32], uint32_t (&v1)[32], uint32_t ibx) {
-        const uint32_t st = ibx % KB_NB;
-        mbar_wait(BAR(D_FULL + st), (ibx / KB_NB) & 1);
+      for (int t = 0; t < nct; ++t, ++ib) {
+        const uint32_t st = ib % KB_NB;
+        mbar_wait(BAR(D_FULL + st), (ib / KB_NB) & 1);
         tc_fence_after();
+        const int64_t c_tile = p.col0 + (int64_t)(ct0 + t) * KB_TN + col_half * 64;
+        const float* hj_t = hj_s + (ib % KB_HJ_SLOTS) * KB_TN + col_half * 64;
         const uint32_t tb = tmem + t_lane + st * 128 + (uint32_t)(col_half * 64);
-        tc_ld32_nowait(tb, v0);
-        tc_ld32_nowait(tb + 32, v1);
-      };
-      auto landed = [&](uint32_t (&v0)[32], uint32_t (&v1)[32], uint32_t ibx) {
-        tc_ld_wait_dep(v0);
-        tc_ld_wait_dep(v1);
-        tc_fence_before();
-        mbar_arrive(BAR(D_EMPTY + ibx % KB_NB));
-      };
-      auto chunk = [&](const uint32_t (&v)[32], const float* hj_c, int64_t c0) {
-        float m[8];
+        // One test per 32 columns instead of one per 4: t = max_c (dot_c - sq_c / 2) > h_i ?  (survivors are rare: ~128 per
+        // row and round).  The next 32 columns are already on their way from TMEM while these are reduced, and the
+        // accumulator is handed back to the MMA warp as soon as the last TMEM read has landed, not after the math.
+        uint32_t va[32], vb[32];
+        auto chunk = [&](uint32_t (&v)[32], uint32_t (&vnext)[32], int ch) {
+          tc_ld_wait_dep(v);
+          if (ch < 1) tc_ld32_nowait(tb + (ch + 1) * 32, vnext);
+          else { tc_fence_before(); mbar_arrive(BAR(D_EMPTY + st)); }
+          float4 h[8];
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          const float4 h = *reinterpret_cast<const float4*>(hj_c + g * 4);
-          m[g] = fmaxf(fmaxf(__uint_as_float(v[g * 4 + 0]) - h.x, __uint_as_float(v[g * 4 + 1]) - h.y),
-                       fmaxf(__uint_as_float(v[g * 4 + 2]) - h.z, __uint_as_float(v[g * 4 + 3]) - h.w));
-        }
-        const float best = fmaxf(fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])), fmaxf(fmaxf(m[4], m[5]), fmaxf(m[6], m[7])));
-        if (best > hi) {               // pass <=> tau > sq_i + sq_j - 2 dot  <=>  dot - sq_j/2 > (sq_i - tau)/2
+          for (int g = 0; g < 8; ++g) h[g] = *reinterpret_cast<const float4*>(hj_t + ch * 32 + g * 4);
+          float m[8];
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            if (m[g] > hi) {
-              const float4 h = *reinterpret_cast<const float4*>(hj_c + g * 4);
-              const float hh[4] = {h.x, h.y, h.z, h.w};
+          for (int g = 0; g < 8; ++g)
+            m[g] = fmaxf(fmaxf(__uint_as_float(v[g * 4 + 0]) - h[g].x, __uint_as_float(v[g * 4 + 1]) - h[g].y),
+                         fmaxf(__uint_as_float(v[g * 4 + 2]) - h[g].z, __uint_as_float(v[g * 4 + 3]) - h[g].w));
+          const float best = fmaxf(fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])), fmaxf(fmaxf(m[4], m[5]), fmaxf(m[6], m[7])));
+          if (best > hi) {               // pass <=> tau > sq_i + sq_j - 2 dot  <=>  dot - sq_j/2 > (sq_i - tau)/2
+            const int64_t c0 = c_tile + ch * 32;
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float dot = __uint_as_float(v[g * 4 + e]);
-                const int64_t j = c0 + g * 4 + e;
-                if ((dot - hh[e]) > hi && j != row)
-                  n_q = knn_park(my_q, n_q, __float_as_uint(sqi + 2.0f * (hh[e] - dot)), (uint32_t)j, p.cnt + lrow,
-                                 p.buf + lrow * KB_CAP, p.overflow);
+            for (int g = 0; g < 8; ++g) {
+              if (m[g] > hi) {
+                const float hh[4] = {h[g].x, h[g].y, h[g].z, h[g].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float dot = __uint_as_float(v[g * 4 + e]);
+                  const int64_t j = c0 + g * 4 + e;
+                  if ((dot - hh[e]) > hi && j != row)
+                    n_q = knn_park(my_q, n_q, __float_as_uint(sqi + 2.0f * (hh[e] - dot)), (uint32_t)j, p.cnt + lrow,
+                                   p.buf + lrow * KB_CAP, p.overflow);
+                }
               }
             }
           }
-        }
-      };
-      auto process = [&](const uint32_t (&v0)[32], const uint32_t (&v1)[32], int t, uint32_t ibx) {
-        const int64_t c_tile = p.col0 + (int64_t)(ct0 + t) * KB_TN + col_half * 64;
-        const float* hj_t = hj_s + (ibx % KB_HJ_SLOTS) * KB_TN + col_half * 64;
-        chunk(v0, hj_t, c_tile);
-        chunk(v1, hj_t + 32, c_tile + 32);
-      };
-      uint32_t a0[32], a1[32], b0[32], b1[32];
-      issue(a0, a1, ib);
-      for (int t = 0; t < nct; t += 2) {
-        landed(a0, a1, ib);
-        if (t + 1 < nct) issue(b0, b1, ib + 1);
-        process(a0, a1, t, ib);
-        if (t + 1 >= nct) { ib += 1; break; }
-        landed(b0, b1, ib + 1);
-        if (t + 2 < nct) issue(a0, a1, ib + 2);
-        process(b0, b1, t + 1, ib + 1);
-        ib += 2;
+        };
+        tc_ld32_nowait(tb, va);
+        chunk(va, vb, 0);
+        chunk(vb, va, 1);
       }
       flush(lrow);
     }
