@@ -9,7 +9,10 @@
 // epilogue, traverse_kernels.cuh).  A one-warp wait kernel and the merge kernel run on the group's own stream, so
 // the exchange + merge of batch i overlaps the search of batch i+1 on the caller's stream; windows are
 // double-buffered and a slot is rewritten only after every rank reported (done flags) that it merged the sequence
-// that used it before.  No host synchronisation anywhere unless the caller asked for host outputs.
+// that used it before: a one-warp back-pressure kernel in front of the final top-k waits for that (never the top-k
+// CTAs themselves -- spinning CTAs that fill every SM keep this GPU's own merge kernel from being scheduled).  No host
+// synchronisation anywhere unless the caller asked for host outputs.  The hand-off is modelled under skewed timings
+// in tests/test_exchange_protocol_model.py.
 //
 //   window (per rank):  flags { arrive[depth][16], done[16] } | depth x { sc [B][G][k] | ids [B][G][k] | st [B][G] }
 
