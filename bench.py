@@ -502,10 +502,14 @@ def run_b200(args, T, rank, world, local_rank):
 
     se = nb.Searcher(ix, sc, B, Ts)
     k_s = Ts[5]
+    # batches in flight (one GPU): searcher j + stream j serve steps j, j+P, ...; every batch is still one whole call
+    P = max(1, args.inflight) if world == 1 else 1
+    ses = [se] + [nb.Searcher(ix, sc, B, Ts) for _ in range(P - 1)]
+    streams = [stream] + [torch.cuda.Stream(device=dev) for _ in range(P - 1)]
     q_dev = torch.from_numpy(queries).to(dev)
     q_pin = torch.from_numpy(queries).pin_memory()
     outs = [(torch.empty((B, k), dtype=torch.int64, device=dev), torch.empty((B, k), dtype=torch.float32, device=dev),
-             torch.empty((B,), dtype=torch.int32, device=dev)) for _ in range(2)]
+             torch.empty((B,), dtype=torch.int32, device=dev)) for _ in range(max(2, P))]
     if world > 1 and grp is None:
         from nann_b200 import distributed as nd
         ids_d = torch.empty((B, k_s), dtype=torch.int64, device=dev)
@@ -515,7 +519,7 @@ def run_b200(args, T, rank, world, local_rank):
         """inputs resident in HBM, results left in HBM, nothing synchronises the host"""
         u = q_dev[i * B:(i + 1) * B]
         if world == 1:
-            se.search_async(u, Ts, *outs[i & 1], stream=stream)
+            ses[i % P].search_async(u, Ts, *outs[i % len(outs)], stream=streams[i % P])
         elif grp is not None:
             grp.search(se, u, Ts, k, *outs[i & 1], stream=stream)
         else:
@@ -532,14 +536,16 @@ def run_b200(args, T, rank, world, local_rank):
     def step_e2e(i):
         # host buffers in, host results out: H2D of the queries and D2H of ids+scores inside the timed region
         if world == 1:
-            return se.search(q_pin[i * B:(i + 1) * B].numpy(), Ts)
+            return ses[i % P].search(q_pin[i * B:(i + 1) * B].numpy(), Ts, stream=streams[i % P])
         return sharded_host(se, q_pin[i * B:(i + 1) * B].numpy(), Ts)
 
     step_wall = []
 
-    def timed(fn, profile, drain=False):
+    def timed(fn, profile, drain=False, threads=1):
         for w in range(args.warmup):
             fn(w)
+        for j in range(P if P > 1 else 0):                  # every searcher in flight has run at least twice
+            fn(j)
         if drain and grp is not None:
             grp.wait()
         barrier()
@@ -550,12 +556,26 @@ def run_b200(args, T, rank, world, local_rank):
         t0 = time.perf_counter()
         timed.window = [t0, t0]
         e0.record(stream)
-        for s in range(args.steps):
+
+        def one(s):
             ts = time.perf_counter()
             fn(args.warmup + s)
             step_wall.append(time.perf_counter() - ts)
+
+        if threads > 1:        # synchronous public calls from `threads` host threads, thread j = searcher j = steps j, j+P, ...
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(threads) as pool:
+                for f in [pool.submit(lambda j=j: [one(s) for s in range(j, args.steps, threads)]) for j in range(threads)]:
+                    f.result()
+        else:
+            for s in range(args.steps):
+                one(s)
         if drain and grp is not None:
             grp.wait(stream=stream, host_block=False)      # the timed region ends when the last merge has run
+        for st_ in streams[1:]:                             # ... and when every stream in flight has drained
+            ev_ = torch.cuda.Event()
+            ev_.record(st_)
+            stream.wait_event(ev_)
         e1.record(stream)
         barrier()
         wall = time.perf_counter() - t0
@@ -575,11 +595,12 @@ def run_b200(args, T, rank, world, local_rank):
     nvl1 = nvlink_tx_rx_kib(local_rank) if (world > 1 and rank == 0) else None
     # stage clocks (scorer launches for the roofline): the same steps with CUDA events around every stage
     prof_ms, _, _, prof = timed(step_profile, True)
-    e2e_dev_ms, e2e_wall_ms, _, _ = timed(step_e2e, False)
+    e2e_dev_ms, e2e_wall_ms, _, _ = timed(step_e2e, False, threads=P)
     # the public call is synchronous (host results are returned), so a step's wall time is the batch latency
     lat = sorted(step_wall)
     latency_ms = {"p50": 1000.0 * lat[len(lat) // 2], "max": 1000.0 * lat[-1], "batch": B,
-                  "what": "wall time of one public API call (host queries in, host ids+scores out)"}
+                  "what": "wall time of one public API call (host queries in, host ids+scores out)" +
+                          (f", {P} such calls in flight on the GPU" if P > 1 else "")}
 
     # ---- recall@k of the measured configuration (outside the timed region)
     try:
@@ -702,10 +723,12 @@ def run_b200(args, T, rank, world, local_rank):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": dict(workload_config(args, T, world), shard_level_topn=Ts, scorer_precision=args.precision),
         "exchange": exchange,
+        "batches_in_flight": P,
         "e2e": {"value": B * args.steps / (e2e_wall_ms / 1000.0), "unit": "queries/s",
                 "h2d_bytes_per_step": B * 128 * 4,
                 "d2h_bytes_per_step": (B * k * 12 + B * 4 + 10 * B * 4) if world == 1 else B * k * 12 + B * 4,
-                "timing": "wall clock around the public API call with pinned host inputs and host outputs",
+                "timing": "wall clock around the public API call with pinned host inputs and host outputs" +
+                          (f" ({P} host threads, one searcher + stream each)" if P > 1 else ""),
                 "device_ms_per_step": e2e_dev_ms / args.steps},
         "latency_ms": latency_ms,
         "gpu_launches": launches,
@@ -968,6 +991,9 @@ def main():
                     help="N>1: shard = own HNSW per GPU + one exchange of per-shard top-k (calibrated beams); dist = one graph, "
                          "embedding table row-sharded, distributed scoring (bit-identical to the one-GPU search)")
     ap.add_argument("--no-replica", action="store_true")
+    ap.add_argument("--inflight", type=int, default=int(os.environ.get("NANN_BENCH_INFLIGHT", "1")),
+                    help="N=1: batches in flight, each on its own searcher + stream (the integer stages of one batch run under "
+                         "the scorer of another; the reference's analogue is BLAZE_THREADS_NUM concurrent runs of one op)")
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--build-index-only", action="store_true", help="build + cache the unsharded index files and exit (offline tooling)")
