@@ -379,7 +379,8 @@ nann_status nann_shard_group_wait(nann_shard_group_t* g, void* stream, int host_
  * with the ordinary scorer kernel, and the scores come back (stores into IPC-mapped peer windows over NVLink + flags,
  * no host synchronisation).  The result is BIT-IDENTICAL to nann_search_batch on the unsharded index; per-GPU scoring
  * work is 1/world of it.  Every rank must call nann_search_distributed with the same B and level_topn (collective);
- * out_* are this rank's queries only.  mlp scorer only.  Device outputs: the call only enqueues on `stream`
+ * out_* are this rank's queries only.  Both scorers (the attention scorer's raw user sequences travel with the key
+ * projections, once per call).  Device outputs: the call only enqueues on `stream`
  * (nann_dist_group_check reports a timed-out exchange); host outputs: it returns when they are filled -- every rank
  * then needs its own thread or process.
  * ---------------------------------------------------------------------------------------- */

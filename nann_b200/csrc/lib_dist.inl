@@ -12,13 +12,16 @@
 // followed by a system-scope flag; waits are one-warp kernels on the same stream, so nothing synchronises the host.
 // Per-GPU work = 1/N of the unsharded rows; cost = 1 + 2 x 5 flag round trips per step.
 //
-//   window (per rank): flags {hu[16], ids[16], sc[16]} | hu_all [G*B][ustate] | req_ids [G*B][cap] | req_cnt [G*B] |
-//                      resp_sc [G*B][cap]           (G = world, B = the call's batch per rank, cap = candidates per query)
+//   window (per rank): flags {hu[16], ids[16], sc[16]} | hu_all [G*B][ustate] | us_all [G*B][uraw] | req_ids [G*B][cap] |
+//                      req_cnt [G*B] | resp_sc [G*B][cap]
+//   (G = world, B = the call's batch per rank, cap = candidates per query; ustate = the per-query state the scorer
+//   precomputes -- the hoisted layer-1 half of the mlp, the key projections of the attention scorer; uraw = the raw user
+//   floats, shared only when the scoring kernel reads them as well: the attention scorer's 50 x 64 sequence)
 
 struct nann_dist_group {
-  int device = 0, rank = 0, world = 1, max_batch = 0, ustate = 0;
+  int device = 0, rank = 0, world = 1, max_batch = 0, ustate = 0, uraw = 0;
   int64_t cap = 0;
-  size_t off_hu = 0, off_req_ids = 0, off_req_cnt = 0, off_resp = 0, window_bytes = 0;
+  size_t off_hu = 0, off_us = 0, off_req_ids = 0, off_req_cnt = 0, off_resp = 0, window_bytes = 0;
   uint8_t* window = nullptr;
   uint8_t* peer[nann::NANN_MAX_SHARDS] = {nullptr};
   bool peer_ipc[nann::NANN_MAX_SHARDS] = {false};
@@ -36,12 +39,17 @@ namespace nann {
 constexpr size_t DIST_FLAG_BYTES = 4096;
 struct DistPeers { int world, rank; uint8_t* win[NANN_MAX_SHARDS]; };
 
-// copy `n` floats to offset dst_off of every rank's window, then publish flag[rank] = epoch everywhere (last CTA)
-__global__ void dist_bcast_kernel(const float* __restrict__ src, int64_t n, DistPeers P, size_t dst_off, unsigned int* counter,
-                                  size_t flag_off, unsigned long long epoch) {
+// copy `n` floats to offset dst_off (and `n2` floats to dst_off2) of every rank's window, then publish
+// flag[rank] = epoch everywhere (last CTA)
+__global__ void dist_bcast_kernel(const float* __restrict__ src, int64_t n, size_t dst_off, const float* __restrict__ src2, int64_t n2,
+                                  size_t dst_off2, DistPeers P, unsigned int* counter, size_t flag_off, unsigned long long epoch) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float v = src[i];
     for (int p = 0; p < P.world; ++p) reinterpret_cast<float*>(P.win[p] + dst_off)[i] = v;
+  }
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = src2[i];
+    for (int p = 0; p < P.world; ++p) reinterpret_cast<float*>(P.win[p] + dst_off2)[i] = v;
   }
   __threadfence_system();
   __syncthreads();
@@ -131,13 +139,13 @@ static DistPeers dist_peers(const nann_dist_group* g) {
   return P;
 }
 
-// users' hoisted state -> every rank (once per call)
-static nann_status dist_share_user_state(nann_dist_group* g, const float* ustate, int B, cudaStream_t st) {
-  const int64_t n = (int64_t)B * g->ustate;
+// the users' precomputed state (and, for the attention scorer, the raw sequences) -> every rank (once per call)
+static nann_status dist_share_user_state(nann_dist_group* g, const float* ustate, const float* users, int B, cudaStream_t st) {
+  const int64_t n = (int64_t)B * g->ustate, n2 = (int64_t)B * g->uraw;
   const unsigned long long epoch = ++g->epoch_hu;
   const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(n, 256), 148 * 2);
-  NANN_LAUNCH(dist_bcast_kernel, grid, 256, 0, st, ustate, n, dist_peers(g), g->off_hu + (size_t)g->rank * B * g->ustate * 4,
-              g->counters + 0, (size_t)0, epoch);
+  NANN_LAUNCH(dist_bcast_kernel, grid, 256, 0, st, ustate, n, g->off_hu + (size_t)g->rank * B * g->ustate * 4, users, n2,
+              g->off_us + (size_t)g->rank * B * g->uraw * 4, dist_peers(g), g->counters + 0, (size_t)0, epoch);
   NANN_LAUNCH(shard_wait_kernel, 1, 32, 0, st, (const unsigned long long*)g->window, g->world, epoch - 1, g->error);
   return NANN_OK;
 }
@@ -160,7 +168,8 @@ static nann_status dist_score_round(nann_searcher* s, nann_dist_group* g, const 
   c.table = ix->emb; c.ids = (const int32_t*)(g->window + g->off_req_ids); c.ids_stride = g->cap; c.rows_stride = 0;
   c.n_ptr = (const int32_t*)(g->window + g->off_req_cnt); c.n_fixed = 0;
   c.max_n = (int)std::min<int64_t>(bound, g->cap); c.B = G * B;
-  c.hu = (const float*)(g->window + g->off_hu); c.users = nullptr;
+  c.hu = (const float*)(g->window + g->off_hu);
+  c.users = g->uraw ? (const float*)(g->window + g->off_us) : nullptr;
   c.out = g->svc_sc; c.out_stride = g->cap; c.status = nullptr;
   c.ws = &g->svc_ws;
   NANN_TRY(scorer_score(s->sc, c, st));
@@ -207,10 +216,12 @@ nann_status nann_dist_group_create(const nann_searcher_t* s, int rank, int world
   auto* g = new nann_dist_group();
   g->device = ix->device; g->rank = rank; g->world = world; g->max_batch = s->max_batch; g->cap = s->maxc;
   g->ustate = (int)scorer_user_state_floats(s->sc);
+  g->uraw = s->sc->kind == 1 ? nann_scorer_user_floats(s->sc) : 0;   // the attention kernel also reads the raw sequence
   auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
   const size_t rows = (size_t)world * g->max_batch;
   g->off_hu = DIST_FLAG_BYTES;
-  g->off_req_ids = g->off_hu + al(rows * g->ustate * 4);
+  g->off_us = g->off_hu + al(rows * g->ustate * 4);
+  g->off_req_ids = g->off_us + al(rows * g->uraw * 4);
   g->off_req_cnt = g->off_req_ids + al(rows * g->cap * 4);
   g->off_resp = g->off_req_cnt + al(rows * 4);
   g->window_bytes = g->off_resp + al(rows * g->cap * 4);
@@ -269,7 +280,8 @@ nann_status nann_dist_group_connect_local(nann_dist_group_t* const* members, int
   for (int r = 0; r < world; ++r) {
     nann_dist_group* g = members[r];
     if (!g || g->world != world || g->rank != r) return fail(NANN_INVALID_ARGUMENT, "members[%d] is not rank %d of %d", r, r, world);
-    if (g->max_batch != members[0]->max_batch || g->cap != members[0]->cap || g->ustate != members[0]->ustate)
+    if (g->max_batch != members[0]->max_batch || g->cap != members[0]->cap || g->ustate != members[0]->ustate ||
+        g->uraw != members[0]->uraw)
       return fail(NANN_INVALID_ARGUMENT, "members differ in batch / candidate capacity / scorer");
   }
   for (int r = 0; r < world; ++r) {
@@ -305,7 +317,8 @@ nann_status nann_search_distributed(nann_searcher_t* s, nann_dist_group_t* g, co
   NANN_TRY(search_check_args(s, users, B, T));
   if (!g->connected) return fail(NANN_FAILED_PRECONDITION, "group is not connected (nann_dist_group_connect)");
   if (g->max_batch != s->max_batch || g->cap != s->maxc) return fail(NANN_INVALID_ARGUMENT, "group was created for another searcher");
-  if (s->sc->kind != 0) return fail(NANN_UNIMPLEMENTED, "distributed scoring is implemented for the mlp scorer (the attention scorer also needs the raw user sequence on every rank)");
+  if (g->ustate != (int)scorer_user_state_floats(s->sc) || g->uraw != (s->sc->kind == 1 ? nann_scorer_user_floats(s->sc) : 0))
+    return fail(NANN_INVALID_ARGUMENT, "group was created for another scorer");
   if (B == 0) return fail(NANN_INVALID_ARGUMENT, "every rank must bring the same, non-zero number of queries");
   cudaStream_t st = (cudaStream_t)stream;
   NANN_CUDA(cudaSetDevice(g->device));

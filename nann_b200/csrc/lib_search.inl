@@ -625,7 +625,7 @@ namespace nann {
 // the searcher's out_sc / out_nodes / out_item ([B][max(k,1)]), per-query status and the per-round counters in
 // s->status / s->round_n / s->round_exp.  `push` (optional) makes the final top-k deliver its records to the shard
 // group's windows as well (lib_shard.inl).
-static nann_status dist_share_user_state(nann_dist_group* g, const float* ustate, int B, cudaStream_t st);
+static nann_status dist_share_user_state(nann_dist_group* g, const float* ustate, const float* users, int B, cudaStream_t st);
 static nann_status dist_score_round(nann_searcher* s, nann_dist_group* g, const int32_t* ids, int64_t ids_stride, const int32_t* n_ptr,
                                     int n_fixed, int64_t bound, int B, cudaStream_t st);
 
@@ -650,7 +650,7 @@ static nann_status search_core(nann_searcher* s, int B, const int32_t T[6], cuda
     NANN_LAUNCH(search_init_kernel, (unsigned)std::min<int64_t>(ceil_div(work, 256), 148 * 4), 256, 0, st, ia);
   }
   NANN_TRY(scorer_prepare_users(s->sc, s->users, B, s->ustate, st));
-  if (s->dist) NANN_TRY(dist_share_user_state(s->dist, s->ustate, B, st));
+  if (s->dist) NANN_TRY(dist_share_user_state(s->dist, s->ustate, s->users, B, st));
 
   s->ev_used = 0;
   auto t_begin = [&](int stage) {

@@ -548,3 +548,65 @@ def test_distributed_scoring_two_members_two_threads(nb, world, precision):
             np.testing.assert_array_equal(id_h, want["ids"][r * B:(r + 1) * B])
             np.testing.assert_array_equal(sc_h.view(np.uint32), want["scores"][r * B:(r + 1) * B].view(np.uint32))
             assert np.all(st_h == 0)
+
+
+def test_distributed_scoring_attention_scorer(nb):
+    """The reference's own scorer (config 1: d=64 f16 table, user [50,64]) through distributed scoring: the key projections
+    AND the raw user sequences travel to the owners.  A group of one, then two members on two threads; ids and scores equal
+    nann_search_batch on the unsharded index bit for bit."""
+    import threading
+    import torch
+    from nann_b200 import scorer_weights as sw
+    from nann_b200.distributed import DistGroup
+    from tests import util
+    w = util.build_world(tag="c1", n=3000, d=64, M=16, m_levels=6, seed=4, n_cand=40, device="cpu")
+    emb16 = w["emb"].astype(np.float16)
+    n = emb16.shape[0]
+    sc = nb.Scorer.attention(sw.attention_blob(seed=3))
+    T = [20, 40, 40, 40, 40, 40]
+    B, G = 3, 2
+    rng = np.random.default_rng(0)
+    users = (0.01 * rng.random((2 * G * B, 3200))).astype(np.float16).astype(np.float32)
+    ix_full = nb.Index.from_arrays(emb16, w["item_ids"], w["ep"], w["values"], w["row_splits"])
+    ref = nb.Searcher(ix_full, sc, G * B, T)
+    # a group of one
+    ix1 = nb.Index.from_arrays_sharded(n, emb16, 0, w["item_ids"], w["ep"], w["values"], w["row_splits"])
+    se1 = nb.Searcher(ix1, sc, G * B, T)
+    g1 = DistGroup(se1, 0, 1)
+    want = ref.search(users[:G * B], T)
+    assert np.all(want["status"] == 0)
+    sc_h, id_h, st_h = g1.search(users[:G * B], T)
+    np.testing.assert_array_equal(id_h, want["ids"])
+    np.testing.assert_array_equal(sc_h.view(np.uint32), want["scores"].view(np.uint32))
+    # two members, two threads
+    per = -(-n // G)
+    members, keep = [], []
+    for r in range(G):
+        lo, hi = r * per, min((r + 1) * per, n)
+        ix = nb.Index.from_arrays_sharded(n, emb16[lo:hi], lo, w["item_ids"], w["ep"], w["values"], w["row_splits"])
+        se = nb.Searcher(ix, sc, B, T)
+        keep.append((ix, se))
+        members.append(DistGroup(se, r, G))
+    DistGroup.connect_local(members)
+    streams = [torch.cuda.Stream() for _ in range(G)]
+    res = [[None] * 2 for _ in range(G)]
+    errs = []
+
+    def drive(r):
+        try:
+            for i in range(2):
+                res[r][i] = members[r].search(users[(i * G + r) * B:(i * G + r + 1) * B], T, stream=streams[r])
+        except Exception as e:                         # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=drive, args=(r,)) for r in range(G)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
+    for i in range(2):
+        want = ref.search(users[i * G * B:(i + 1) * G * B], T)
+        for r in range(G):
+            sc_h, id_h, st_h = res[r][i]
+            np.testing.assert_array_equal(id_h, want["ids"][r * B:(r + 1) * B])
+            np.testing.assert_array_equal(sc_h.view(np.uint32), want["scores"][r * B:(r + 1) * B].view(np.uint32))
+            assert np.all(st_h == 0)
