@@ -944,11 +944,8 @@ nann_status nann_search_batch(nann_searcher_t* s, const float* users, int B, con
   const nann_index* ix = s->ix;
   cudaStream_t st = (cudaStream_t)stream;
   NANN_CUDA(cudaSetDevice(ix->device));
-  const int64_t mb = s->max_batch;
-  const int k = T[5];
   NANN_TRY(search_enqueue(s, users, B, T, st, nullptr));
-
-  return search_deliver(s, B, k, out_item_ids, out_scores, out_status, stats, st);
+  return search_deliver(s, B, T[5], out_item_ids, out_scores, out_status, stats, st);
 }
 
 nann_status nann_searcher_get_trace(nann_searcher_t* s, int q, int round, int32_t* ids, float* scores,
