@@ -8,7 +8,6 @@ Two forms, same results:
 """
 import ctypes as C
 import math
-import os
 
 import numpy as np
 

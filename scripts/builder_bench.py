@@ -5,7 +5,7 @@ import time
 import torch
 
 sys.path.insert(0, __file__.rsplit("/", 2)[0])
-from nann_b200 import builder, index as nix  # noqa: E402
+from nann_b200 import builder  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2

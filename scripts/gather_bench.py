@@ -5,7 +5,7 @@ With NCU_ONE=1 only one warm call + one measured call run (for `ncu --set full -
 import ctypes as C, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-import nann_b200 as nb
+import nann_b200  # noqa: F401  (loads the library)
 from nann_b200 import _lib
 
 n_rows, d = int(os.environ.get("ROWS", 10_000_000)), 128

@@ -1,7 +1,7 @@
 """Static evidence from the built library (no GPU needed): per-kernel registers / stack, and the Blackwell SASS
 mnemonics (tcgen05 = UTC*, TMEM loads = LDTM, TMA-engine bulk copies = UBLKCP, mbarrier = SYNCS) per kernel.
 usage: python scripts/sass_summary.py > profiles/r02_sass_summary.txt"""
-import collections, os, re, subprocess, sys
+import collections, os, re, subprocess
 so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "nann_b200", "lib", "libnann_b200.so")
 res = subprocess.run(["cuobjdump", "-res-usage", so], capture_output=True, text=True).stdout
 sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout

@@ -1,8 +1,7 @@
 """BASELINE configs[4]: dynamic-batch latency/throughput sweep 1..4096 queries on the 1M corpus
 (blaze-benchmark parity): closed-loop executor, predictor_num searchers x max_batch_size."""
-import json, os, sys, time
+import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np
 import nann_b200 as nb
 from nann_b200 import harness, index as nix, scorer_weights as sw
 import bench

@@ -6,7 +6,6 @@ import os
 import socket
 
 import numpy as np
-import pytest
 
 
 def _free_port():
