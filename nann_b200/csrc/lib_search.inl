@@ -528,6 +528,7 @@ struct nann_searcher {
   };
   struct GraphVal { cudaGraphExec_t exec = nullptr; uint64_t kernels = 0; };   // kernels per replay (for the launch counter)
   std::map<GraphKey, GraphVal> graphs;
+  cudaStream_t own_stream = nullptr;   // for host-in / host-out calls on the NULL stream (which cannot be captured), lazily
   // host mirrors of the last call
   std::vector<int32_t> h_round_n, h_round_exp, h_status;
   int last_B = 0, last_k = 0;
@@ -551,6 +552,7 @@ void nann_searcher_destroy(nann_searcher_t* s) {
   cudaFree(s->out_item); cudaFree(s->status); cudaFree(s->tr_ids); cudaFree(s->tr_sc);
   for (auto e : s->ev) cudaEventDestroy(e);
   for (auto& kv : s->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  if (s->own_stream) cudaStreamDestroy(s->own_stream);
   if (s->tcws) { nann::tc_ws_free(s->tcws); delete s->tcws; }
   delete s;
 }
@@ -797,6 +799,11 @@ static nann_status search_core(nann_searcher* s, int B, const int32_t T[6], cuda
 // (B, level_topn, precision) key is captured into a CUDA graph the second time the key is seen (the first call runs
 // eagerly and sizes every lazily grown buffer) and replayed with ONE launch afterwards.  Not used while tracing or
 // profiling (those add per-call work) or for the sharded push (its arguments carry the sequence number).
+static int search_graph_max_batch() {
+  static const int v = [] { const char* e = std::getenv("NANN_GRAPH_MAX_BATCH"); return e ? atoi(e) : 32; }();
+  return v;
+}
+
 static nann_status search_enqueue(nann_searcher* s, const float* users, int B, const int32_t T[6], cudaStream_t st,
                                   const ShardPush* push) {
   const int uf = nann_scorer_user_floats(s->sc);
@@ -805,8 +812,10 @@ static nann_status search_enqueue(nann_searcher* s, const float* users, int B, c
   else
     NANN_CUDA(cudaMemcpyAsync(s->users, users, (size_t)B * uf * 4, cudaMemcpyHostToDevice, st));
   s->last_B = B; s->last_k = T[5];
-  static const int graph_max_b = [] { const char* e = std::getenv("NANN_GRAPH_MAX_BATCH"); return e ? atoi(e) : 32; }();
-  if (push || s->dist || s->trace || s->profile || B > graph_max_b) return search_core(s, B, T, st, push);
+  const int graph_max_b = search_graph_max_batch();
+  // (the legacy default stream cannot be captured: eager there, without provoking the error on every call)
+  if (push || s->dist || s->trace || s->profile || B > graph_max_b || st == nullptr || st == cudaStreamLegacy)
+    return search_core(s, B, T, st, push);
   nann_searcher::GraphKey key{};
   key.B = B; key.precision = s->sc->precision;
   for (int i = 0; i < 6; ++i) key.T[i] = T[i];
@@ -820,7 +829,8 @@ static nann_status search_enqueue(nann_searcher* s, const float* users, int B, c
     const uint64_t l0 = g_launches.load(std::memory_order_relaxed);
     if (cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
       cudaGetLastError();
-      return search_core(s, B, T, st, push);      // e.g. the legacy default stream cannot be captured
+      s->graphs.erase(it);                         // this stream cannot be captured: do not try again on every call
+      return search_core(s, B, T, st, push);
     }
     const nann_status rc = search_core(s, B, T, st, push);
     const cudaError_t e = cudaStreamEndCapture(st, &graph);
@@ -944,6 +954,18 @@ nann_status nann_search_batch(nann_searcher_t* s, const float* users, int B, con
   const nann_index* ix = s->ix;
   cudaStream_t st = (cudaStream_t)stream;
   NANN_CUDA(cudaSetDevice(ix->device));
+  // The reference's operating mode -- a small batch, host tensors in and out, no stream given (what the TF shim and the
+  // serving front-end do): such a call synchronises before it returns and depends on no earlier GPU work, so it may run on
+  // a stream of the searcher's own, where the launch sequence replays as a CUDA graph (the NULL stream cannot be captured).
+  if ((st == nullptr || st == cudaStreamLegacy) && B <= search_graph_max_batch() && !is_device_ptr(users)) {
+    const bool any_dev = (out_item_ids && is_device_ptr(out_item_ids)) || (out_scores && is_device_ptr(out_scores)) ||
+                         (out_status && is_device_ptr(out_status));
+    const bool will_sync = out_item_ids || out_scores || out_status || stats;
+    if (!any_dev && will_sync) {
+      if (!s->own_stream) NANN_CUDA(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
+      st = s->own_stream;
+    }
+  }
   NANN_TRY(search_enqueue(s, users, B, T, st, nullptr));
   return search_deliver(s, B, T[5], out_item_ids, out_scores, out_status, stats, st);
 }

@@ -466,6 +466,41 @@ def test_small_batches_replay_a_cuda_graph_bit_identically(nb, world):
         world["scorer"].set_precision(nb.SCORER_EXACT)
 
 
+def test_host_calls_without_a_stream_replay_graphs_too(nb, world):
+    """The reference's operating mode: batch 1, host arrays in and out, no stream argument (the NULL stream cannot be
+    captured).  Such calls run on a stream of the searcher's own and replay the captured sequence; every call returns the
+    oracle's result bit for bit, mixed with calls on a caller stream and with device inputs on the NULL stream, and the
+    replayed calls are faster than the launch-bound eager ones."""
+    import time
+    import torch
+    T = world["T"]
+    se = nb.Searcher(world["ix"], world["scorer"], 8, T)
+    side = torch.cuda.Stream()
+    for rep in range(6):
+        for B in (1, 2):
+            users = world["queries"][40 + rep * 2:40 + rep * 2 + B]
+            want = _oracle_batch(world, users, T)
+            for got in (se.search(users, T), se.search(users, T, stream=side), se.search(torch.from_numpy(users).cuda(), T)):
+                np.testing.assert_array_equal(got["ids"], want["ids"])
+                np.testing.assert_array_equal(got["scores"].view(np.uint32), want["scores"].view(np.uint32))
+    users = world["queries"][:1]
+
+    def median_ms(**kw):
+        ts = []
+        for _ in range(30):
+            t0 = time.perf_counter()
+            se.search(users, T, **kw)
+            ts.append(time.perf_counter() - t0)
+        return 1e3 * sorted(ts)[len(ts) // 2]
+
+    replay = median_ms()
+    se.set_trace(True)                                   # tracing disables the graph path: the eager launch sequence
+    eager = median_ms()
+    se.set_trace(False)
+    print(f"batch-1 host call without a stream: {replay:.3f} ms replayed, {eager:.3f} ms eager")
+    assert replay < 0.8 * eager
+
+
 @pytest.mark.parametrize("precision", ["exact", "tensor"])
 def test_distributed_scoring_world1_is_bit_identical_to_the_plain_search(nb, world, precision):
     """nann_search_distributed with a group of ONE: every candidate is owned by this rank, but the whole exchange path
