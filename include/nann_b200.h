@@ -34,6 +34,9 @@
  *   - Streams: `stream` is a cudaStream_t passed as void* (NULL = default stream).  Calls that
  *     hand results back to host memory synchronise that stream before returning; nann_search_batch and
  *     nann_search_sharded with all-device outputs (and no host-side stats) only enqueue work.
+ *     A small-batch nann_search_batch call with stream == NULL and only HOST pointers runs on a stream of the searcher's
+ *     own (so that its launch sequence can replay as a CUDA graph; the NULL stream cannot be captured); it synchronises
+ *     before returning, like every call with host outputs.
  *   - Data-dependent output sizes (GroupGather, BitmapRefDifference) use an allocator callback,
  *     the C equivalent of OpKernelContext::allocate_output: the library calls
  *     alloc(ctx, output_index, n_elems) once per output and writes n_elems elements there.
