@@ -249,7 +249,7 @@ struct MlpTcArgs {
   const float* b2; const float* w3;
   uint8_t* scratch;       // [gridDim.x][TC_SCRATCH_BYTES]
   float* out; int64_t out_stride; const int32_t* status;
-  const int2* tiles; const int32_t* tile_total;   // dense tile list (mlp_tc3_kernel)
+  const int2* tiles; const int32_t* tile_total;   // dense tile list (tile_scan_kernel + tile_fill_kernel)
   long long* trace;                               // optional CTA-0 timeline [64 tiles][48 events] (debug)
   // b2 / w3 by value: kernel parameters live in the constant bank, so the layer-2 epilogue reads them with
   // uniform constant loads.  (With ~225 KB of shared memory per CTA the L1 data cache is a few KB: __ldg of
