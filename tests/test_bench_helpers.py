@@ -73,3 +73,45 @@ def test_per_beam_shard_scales():
     t = shard_beams(T, 8, [1.0837, 1.275, 1.5, 1.5, 0.2953])
     assert t == [14, 32, 38, 38, 8, 50]                  # the beams of the N = 8 and 100M runs (profiles/r02_bench_8gpu_sharded.json)
     assert all(x >= 8 for x in t[:5]) and t[5] <= sum(t[1:5]) and 8 * t[5] >= T[5]
+
+
+def _lines(name):
+    with open(os.path.join(ROOT, "profiles", name)) as f:
+        return [json.loads(l) for l in f if l.strip().startswith("{")]
+
+
+def test_committed_bench_lines_carry_the_whole_contract():
+    """the bench lines kept under profiles/ (what DESIGN.md quotes) have every key of the bench contract, and the numbers
+    inside are consistent with each other"""
+    base = ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+            "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline")
+    one = _lines("r02_bench_1gpu.json")[-1]
+    for k in base:
+        assert k in one, k
+    assert one["n_gpus"] == 1 and one["higher_is_better"] is True and one["vs_baseline"] is None and one["data"] == "synthetic"
+    assert "workload" in one["config"] and "configs[1]" in one["config"]["workload"] and "l2" in one["config"]
+    assert one["gpu_launches"] > 0 and one["warmup"] >= 3
+    # value = batch * steps / device time
+    assert abs(one["value"] - 256 * one["steps"] / (one["ms_per_step"] * one["steps"] / 1e3)) < 1e-6 * one["value"]
+    e = one["e2e"]
+    assert e["h2d_bytes_per_step"] == 256 * 128 * 4 and e["d2h_bytes_per_step"] > 256 * 200 * 12 and 0 < e["value"] <= one["value"] * 1.02
+    r = one["roofline"]
+    assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["traffic"] > 0
+    assert abs(r["achieved"] - r["rows_per_launch"] * r["algorithmic_flops_per_row"] / (r["avg_launch_ms"] / 1e3) / 1e12) < 1e-6 * r["achieved"]
+    c = one["cpu_baseline"]
+    assert c["kind"] == "port" and c["cores"] >= 1 and c["unit"] == one["unit"] and c["sample"] and c["value"] > 0
+    assert c["exact_path_ids_equal_to_cpu"] and c["exact_path_scores_bit_equal"]        # parity side check of the bench itself
+    assert set(one["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    assert not ({"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(one["clocks"]["reasons"]))
+    ref = _lines("r02_bench_reference.json")[-1]
+    assert ref["impl"] == "reference" and ref["config"]["workload"] == one["config"]["workload"] and ref["metric"] == one["metric"]
+    assert ref["e2e"]["h2d_bytes_per_step"] == 0 and ref["e2e"]["value"] == ref["value"] and ref["cpu_baseline"]["kind"] == "port"
+    for n in (2, 4, 8):
+        d = _lines(f"r02_bench_{n}gpu_dist.json")[-1]
+        for k in base:
+            assert k in d, (n, k)
+        assert d["n_gpus"] == n and d["scaling"] == "weak" and d["ids_bit_identical_to_one_gpu_search"] is True and d["recall_held"] is True
+        assert d["gpu_launches"] > 0
+        s = _lines(f"r02_bench_{n}gpu_sharded.json")[-1]
+        assert s["replica_mode"]["value"] > 0            # the replica curve of the same box
+        assert s["n_gpus"] == n and s["recall_held"] is True and abs(s["recall_at_k_vs_bruteforce"] - s["recall_target"]) <= 0.005 + 1e-9
